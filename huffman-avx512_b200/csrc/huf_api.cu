@@ -1,0 +1,534 @@
+// huf_api.cu -- the extern "C" ABI declared in include/hufb200.h.
+//
+// Host entry points move the caller's HOST buffers through a per-thread device
+// workspace (grow-only) and run the same kernels as the *_dev entry points.
+// There is no CPU implementation of any codec step in this file: without a
+// device every compute call fails.
+#include "../../include/hufb200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "huf_kernels.h"
+
+namespace {
+
+using namespace hufb200;
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(expr)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver           \
+                      ? HUFB200_E_NODEVICE                                               \
+                      : HUFB200_E_CUDA,                                                  \
+                  "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+  } while (0)
+
+// Grow-only device buffer owned by the calling host thread.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int dev = -1;
+  cudaError_t reserve(size_t n) {
+    int cur = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return e;
+    if (p && (cur != dev || n > cap)) {
+      cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    if (!p) {
+      size_t want = n < 256 ? 256 : n;
+      want = (want + 255) & ~(size_t)255;
+      e = cudaMalloc(&p, want);
+      if (e != cudaSuccess) {
+        p = nullptr;
+        return e;
+      }
+      cap = want;
+      dev = cur;
+    }
+    return cudaSuccess;
+  }
+  template <typename T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Workspace {
+  DevBuf in, out, sizes, offsets, misc, table;
+};
+thread_local Workspace g_ws;
+
+struct DevInfo {
+  int dev = -1;
+  int sms = 0;
+};
+thread_local DevInfo g_dev;
+
+int sm_count(int* sms) {
+  int cur = 0;
+  CU(cudaGetDevice(&cur));
+  if (g_dev.dev != cur) {
+    int n = 0;
+    CU(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, cur));
+    g_dev.dev = cur;
+    g_dev.sms = n;
+  }
+  *sms = g_dev.sms;
+  return HUFB200_OK;
+}
+
+bool valid_k(int k) { return k >= 1 && k <= HUFB200_MAX_K; }
+
+constexpr size_t kMaxBlock = (size_t)1 << 30;  // offsets are 32-bit inside a buffer (codec/huffman.cpp:772)
+constexpr uint32_t kMagic = 0x32424648u;        // "HFB2"
+constexpr size_t kContainerHeader = 32;
+
+// blocks per decode CTA: fill whole warps with K-lane groups where K divides 32
+int decode_bpc(int k) {
+  if (k >= 32) return (k % 32 == 0) ? 1 : (k == 48 ? 2 : 1);
+  int bpc = 32 / k;
+  return bpc < 1 ? 1 : (bpc > 8 ? 8 : bpc);
+}
+
+int compress_grid(uint32_t n_blocks, int sms) {
+  // 41.8 KB static smem + 512 threads: up to 4 CTAs per SM
+  const uint32_t cap = (uint32_t)sms * 4u;
+  return (int)(n_blocks < cap ? n_blocks : cap);
+}
+
+int do_compress_dev(int k, size_t block_size, const uint8_t* d_raw, size_t n, uint32_t n_blocks,
+                    uint8_t* d_out, size_t slot_stride, uint32_t* d_sizes, const void* d_table,
+                    int check_presence, uint32_t* d_status, cudaStream_t st) {
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  CU(launch_compress(d_raw, n, (uint32_t)block_size, k, n_blocks, d_out, slot_stride, d_sizes, d_table,
+                     check_presence, d_status, compress_grid(n_blocks, sms), st));
+  if (n_blocks) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return HUFB200_OK;
+}
+
+// compress one host buffer as `n_blocks` blocks into the workspace; sizes come back in `sizes`
+int compress_host(int k, size_t block_size, const uint8_t* raw, size_t n, uint32_t n_blocks,
+                  const void* d_table, int check_presence, std::vector<uint32_t>* sizes,
+                  size_t* slot_stride_out) {
+  Workspace& ws = g_ws;
+  const size_t stride = hufb200_slot_stride(block_size, k);
+  CU(ws.in.reserve(n + 16));
+  CU(ws.out.reserve(stride * n_blocks));
+  CU(ws.sizes.reserve(sizeof(uint32_t) * (n_blocks + 1)));
+  CU(ws.misc.reserve(256));
+  if (n) CU(cudaMemcpyAsync(ws.in.p, raw, n, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemsetAsync(ws.misc.p, 0, 4, 0));
+  int rc = do_compress_dev(k, block_size, ws.in.as<uint8_t>(), n, n_blocks, ws.out.as<uint8_t>(), stride,
+                           ws.sizes.as<uint32_t>(), d_table, check_presence, ws.misc.as<uint32_t>(), 0);
+  if (rc) return rc;
+  sizes->resize(n_blocks);
+  uint32_t status = 0;
+  CU(cudaMemcpyAsync(sizes->data(), ws.sizes.p, sizeof(uint32_t) * n_blocks, cudaMemcpyDeviceToHost, 0));
+  CU(cudaMemcpyAsync(&status, ws.misc.p, 4, cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  if (status) return fail(HUFB200_E_CORRUPT, "a symbol of the input has no code in the supplied table");
+  *slot_stride_out = stride;
+  return HUFB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hufb200_version(void) { return 100; }
+const char* hufb200_last_error(void) { return g_err; }
+uint64_t hufb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hufb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------ histogram */
+
+int hufb200_histogram_dev(const uint8_t* d_in, size_t n, uint64_t* d_out, void* stream) {
+  if (!d_out || (!d_in && n)) return fail(HUFB200_E_INVALID, "null pointer");
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  // 32 KB of bins + 512 threads per CTA: 4 CTAs per SM saturate the shared-memory atomics
+  uint64_t want = (n + 65535) / 65536;
+  int grid = (int)(want < (uint64_t)sms * 4 ? (want ? want : 1) : (uint64_t)sms * 4);
+  CU(launch_histogram(d_in, n, reinterpret_cast<unsigned long long*>(d_out), grid, (cudaStream_t)stream));
+  if (n) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return HUFB200_OK;
+}
+
+int hufb200_histogram64(const uint8_t* in, size_t n, uint64_t out[256]) {
+  if (!out || (!in && n)) return fail(HUFB200_E_INVALID, "null pointer");
+  Workspace& ws = g_ws;
+  CU(ws.in.reserve(n + 16));
+  CU(ws.misc.reserve(256 * sizeof(uint64_t)));
+  if (n) CU(cudaMemcpyAsync(ws.in.p, in, n, cudaMemcpyHostToDevice, 0));
+  int rc = hufb200_histogram_dev(ws.in.as<uint8_t>(), n, ws.misc.as<uint64_t>(), nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, ws.misc.p, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  return HUFB200_OK;
+}
+
+int hufb200_histogram(const uint8_t* in, size_t n, uint32_t out[256]) {
+  if (n >> 32) return fail(HUFB200_E_INVALID, "n >= 2^32 does not fit ByteHistogram; use hufb200_histogram64");
+  uint64_t h[256];
+  int rc = hufb200_histogram64(in, n, h);
+  if (rc) return rc;
+  for (int i = 0; i < 256; ++i) out[i] = (uint32_t)h[i];
+  return HUFB200_OK;
+}
+
+/* ---------------------------------------------------------------- table build */
+
+size_t hufb200_table_bytes(void) { return table_bytes(); }
+
+int hufb200_build_table_dev(const uint64_t* d_hist, void* d_table, void* stream) {
+  if (!d_hist || !d_table) return fail(HUFB200_E_INVALID, "null pointer");
+  CU(launch_build_table(reinterpret_cast<const unsigned long long*>(d_hist), d_table, (cudaStream_t)stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return HUFB200_OK;
+}
+
+namespace {
+// mirrors hufb200::HufTable (huf_device.cuh) for the host-side dump
+struct HostTable {
+  uint32_t enc[256];
+  uint8_t sorted_syms[256];
+  uint16_t len_count[16];
+  uint32_t len_mask;
+  int32_t num_syms;
+  uint32_t hdr_len;
+  uint32_t pad_;
+};
+}  // namespace
+
+int hufb200_make_table(const uint32_t hist[256], uint16_t len_count[13], uint8_t sorted_syms[256],
+                       int* num_syms, uint32_t* len_mask, uint16_t code_bits[256], uint16_t code_len[256]) {
+  if (!hist) return fail(HUFB200_E_INVALID, "null pointer");
+  if (sizeof(HostTable) != table_bytes()) return fail(HUFB200_E_INVALID, "table layout mismatch");
+  Workspace& ws = g_ws;
+  CU(ws.misc.reserve(256 * sizeof(uint32_t)));
+  CU(ws.table.reserve(table_bytes()));
+  CU(cudaMemcpyAsync(ws.misc.p, hist, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
+  CU(launch_make_table(ws.misc.as<uint32_t>(), nullptr, nullptr, 0, 0, ws.table.p, 0));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  HostTable t;
+  CU(cudaMemcpyAsync(&t, ws.table.p, sizeof(t), cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  if (len_count)
+    for (int i = 0; i <= HUFB200_MAX_CODE_LEN; ++i) len_count[i] = t.len_count[i];
+  if (sorted_syms) {
+    memset(sorted_syms, 0, 256);
+    memcpy(sorted_syms, t.sorted_syms, (size_t)t.num_syms);
+  }
+  if (num_syms) *num_syms = t.num_syms;
+  if (len_mask) *len_mask = t.len_mask;
+  for (int c = 0; c < 256; ++c) {
+    const uint32_t e = t.enc[c];
+    const bool present = e != 0x40000000u;
+    const uint32_t l = present ? (e >> 16) : 0;
+    // BitCode.bits is left-aligned in 12 bits (codec/huffman.cpp:214-224)
+    if (code_bits) code_bits[c] = present ? (uint16_t)((e & 0xffffu) << (HUFB200_MAX_CODE_LEN - l)) : 0;
+    if (code_len) code_len[c] = (uint16_t)l;
+  }
+  return HUFB200_OK;
+}
+
+int hufb200_decode_table(const uint16_t len_count[13], const uint8_t* sorted_syms, int num_syms,
+                         uint8_t out[4096 * 4]) {
+  if (!len_count || !out || num_syms < 0 || num_syms > 256 || (!sorted_syms && num_syms))
+    return fail(HUFB200_E_INVALID, "bad table arguments");
+  Workspace& ws = g_ws;
+  CU(ws.misc.reserve(1024));
+  CU(ws.out.reserve(4096 * 4));
+  uint8_t* d_lc = ws.misc.as<uint8_t>();
+  uint8_t* d_sy = d_lc + 64;
+  CU(cudaMemcpyAsync(d_lc, len_count, 13 * sizeof(uint16_t), cudaMemcpyHostToDevice, 0));
+  if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, 0));
+  CU(launch_dump_dtable(reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, ws.out.as<uint8_t>(), 0));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CU(cudaMemcpyAsync(out, ws.out.p, 4096 * 4, cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  return HUFB200_OK;
+}
+
+/* -------------------------------------------------------------- single buffer */
+
+size_t hufb200_compress_bound(size_t n, int k) {
+  if (k < 1) k = 1;
+  return 8 + 13 + 256 + 4 * (size_t)(k - 1) + (n * HUFB200_MAX_CODE_LEN + 7) / 8 + (size_t)k * 9;
+}
+
+size_t hufb200_slot_stride(size_t block_size, int k) {
+  return (hufb200_compress_bound(block_size, k) + 4 + 255) & ~(size_t)255;
+}
+
+int hufb200_compress(int k, const uint8_t* raw, size_t n, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
+  if (n > kMaxBlock) return fail(HUFB200_E_INVALID, "n=%zu exceeds the 2^30 single-buffer limit", n);
+  if (!out_len || (!raw && n) || (!out && cap)) return fail(HUFB200_E_INVALID, "null pointer");
+  std::vector<uint32_t> sizes;
+  size_t stride = 0;
+  int rc = compress_host(k, n ? n : 1, raw, n, 1, nullptr, 0, &sizes, &stride);
+  if (rc) return rc;
+  *out_len = sizes[0];
+  if (sizes[0] > cap) return fail(HUFB200_E_NOSPACE, "need %u bytes, have %zu", sizes[0], cap);
+  CU(cudaMemcpy(out, g_ws.out.p, sizes[0], cudaMemcpyDeviceToHost));
+  return HUFB200_OK;
+}
+
+int hufb200_compress_with_table(int k, const uint8_t* raw, size_t n, const uint16_t len_count[13],
+                                const uint8_t* sorted_syms, int num_syms, uint8_t* out, size_t cap,
+                                size_t* out_len) {
+  if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
+  if (n > kMaxBlock) return fail(HUFB200_E_INVALID, "n=%zu exceeds the 2^30 single-buffer limit", n);
+  if (!out_len || (!raw && n) || !len_count || num_syms < 0 || num_syms > 256 || (!sorted_syms && num_syms))
+    return fail(HUFB200_E_INVALID, "bad arguments");
+  Workspace& ws = g_ws;
+  CU(ws.misc.reserve(1024));
+  CU(ws.table.reserve(table_bytes()));
+  uint8_t* d_lc = ws.misc.as<uint8_t>() + 256;
+  uint8_t* d_sy = d_lc + 64;
+  CU(cudaMemcpyAsync(d_lc, len_count, 13 * sizeof(uint16_t), cudaMemcpyHostToDevice, 0));
+  if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, 0));
+  CU(launch_make_table(nullptr, reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, 1, ws.table.p, 0));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  std::vector<uint32_t> sizes;
+  size_t stride = 0;
+  int rc = compress_host(k, n ? n : 1, raw, n, 1, ws.table.p, 1, &sizes, &stride);
+  if (rc) return rc;
+  *out_len = sizes[0];
+  if (sizes[0] > cap) return fail(HUFB200_E_NOSPACE, "need %u bytes, have %zu", sizes[0], cap);
+  CU(cudaMemcpy(out, g_ws.out.p, sizes[0], cudaMemcpyDeviceToHost));
+  return HUFB200_OK;
+}
+
+int hufb200_raw_size(const uint8_t* comp, size_t n, size_t* raw_size) {
+  if (!comp || n < 8 || !raw_size) return fail(HUFB200_E_CORRUPT, "compressed buffer shorter than its header");
+  uint32_t v;
+  memcpy(&v, comp, 4);
+  *raw_size = v;
+  return HUFB200_OK;
+}
+
+int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
+  if (!out_len) return fail(HUFB200_E_INVALID, "null pointer");
+  size_t raw_size = 0;
+  int rc = hufb200_raw_size(comp, n, &raw_size);
+  if (rc) return rc;
+  if (n >> 32) return fail(HUFB200_E_INVALID, "compressed size does not fit 32 bits");
+  *out_len = raw_size;
+  if (raw_size > cap) return fail(HUFB200_E_NOSPACE, "need %zu bytes, have %zu", raw_size, cap);
+  if (raw_size > kMaxBlock) return fail(HUFB200_E_INVALID, "raw_size exceeds the 2^30 single-buffer limit");
+  Workspace& ws = g_ws;
+  CU(ws.in.reserve(n + 32));
+  CU(ws.out.reserve(raw_size + 16));
+  CU(ws.misc.reserve(256));
+  CU(cudaMemcpyAsync(ws.in.p, comp, n, cudaMemcpyHostToDevice, 0));
+  struct {
+    unsigned long long off;
+    uint32_t size;
+    uint32_t status;
+  } meta = {0ull, (uint32_t)n, 0u};
+  CU(cudaMemcpyAsync(ws.misc.p, &meta, sizeof(meta), cudaMemcpyHostToDevice, 0));
+  uint8_t* m = ws.misc.as<uint8_t>();
+  CU(launch_decompress(ws.in.as<uint8_t>(), reinterpret_cast<unsigned long long*>(m),
+                       reinterpret_cast<uint32_t*>(m + 8), 1, k, 1, ws.out.as<uint8_t>(), raw_size,
+                       (uint32_t)(raw_size ? raw_size : 1), reinterpret_cast<uint32_t*>(m + 12), 0));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  uint32_t status = 0;
+  CU(cudaMemcpyAsync(&status, m + 12, 4, cudaMemcpyDeviceToHost, 0));
+  if (raw_size) CU(cudaMemcpyAsync(out, ws.out.p, raw_size, cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  if (status) return fail(HUFB200_E_CORRUPT, "malformed compressed buffer");
+  return HUFB200_OK;
+}
+
+/* ------------------------------------------------------------ block container */
+
+size_t hufb200_blocks_count(size_t n, size_t block_size) {
+  return block_size ? (n + block_size - 1) / block_size : 0;
+}
+
+size_t hufb200_container_bound(size_t n, size_t block_size, int k) {
+  const size_t nb = hufb200_blocks_count(n, block_size);
+  return kContainerHeader + 4 * nb + nb * hufb200_compress_bound(block_size, k);
+}
+
+int hufb200_compress_blocks(int k, size_t block_size, const uint8_t* raw, size_t n, uint8_t* out, size_t cap,
+                            size_t* out_len) {
+  if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
+  if (block_size == 0 || block_size > kMaxBlock) return fail(HUFB200_E_INVALID, "block_size outside 1..2^30");
+  if (block_size % 16) return fail(HUFB200_E_INVALID, "block_size must be a multiple of 16");
+  if (!out_len || (!raw && n) || (!out && cap)) return fail(HUFB200_E_INVALID, "null pointer");
+  const size_t nb = hufb200_blocks_count(n, block_size);
+  if (nb >> 31) return fail(HUFB200_E_INVALID, "too many blocks");
+  std::vector<uint32_t> sizes;
+  size_t stride = 0;
+  int rc = compress_host(k, block_size, raw, n, (uint32_t)nb, nullptr, 0, &sizes, &stride);
+  if (rc) return rc;
+  size_t total = kContainerHeader + 4 * nb;
+  for (size_t b = 0; b < nb; ++b) total += sizes[b];
+  *out_len = total;
+  if (total > cap) return fail(HUFB200_E_NOSPACE, "need %zu bytes, have %zu", total, cap);
+  // header: magic, version|k, block_size, raw_size(u64), n_blocks, reserved
+  memset(out, 0, kContainerHeader);
+  const uint32_t magic = kMagic, vk = 1u | ((uint32_t)k << 16), bs = (uint32_t)block_size, nb32 = (uint32_t)nb;
+  const uint64_t rs = n;
+  memcpy(out + 0, &magic, 4);
+  memcpy(out + 4, &vk, 4);
+  memcpy(out + 8, &bs, 4);
+  memcpy(out + 12, &nb32, 4);
+  memcpy(out + 16, &rs, 8);
+  if (nb) memcpy(out + kContainerHeader, sizes.data(), 4 * nb);
+  // pack on the device, one D2H copy of the payload
+  Workspace& ws = g_ws;
+  const size_t payload = total - kContainerHeader - 4 * nb;
+  if (nb) {
+    CU(ws.offsets.reserve(sizeof(uint64_t) * (nb + 1)));
+    CU(ws.in.reserve(payload + 16));  // the raw input is no longer needed
+    CU(launch_pack(ws.out.as<uint8_t>(), stride, ws.sizes.as<uint32_t>(), (uint32_t)nb, ws.in.as<uint8_t>(),
+                   ws.offsets.as<unsigned long long>(), ws.offsets.as<unsigned long long>() + nb, 0));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    CU(cudaMemcpy(out + kContainerHeader + 4 * nb, ws.in.p, payload, cudaMemcpyDeviceToHost));
+  }
+  return HUFB200_OK;
+}
+
+int hufb200_container_info(const uint8_t* c, size_t n, int* k, size_t* block_size, size_t* raw_size,
+                           size_t* n_blocks) {
+  if (!c || n < kContainerHeader) return fail(HUFB200_E_CORRUPT, "container shorter than its header");
+  uint32_t magic, vk, bs, nb;
+  uint64_t rs;
+  memcpy(&magic, c, 4);
+  memcpy(&vk, c + 4, 4);
+  memcpy(&bs, c + 8, 4);
+  memcpy(&nb, c + 12, 4);
+  memcpy(&rs, c + 16, 8);
+  if (magic != kMagic || (vk & 0xffff) != 1) return fail(HUFB200_E_CORRUPT, "bad container magic/version");
+  const int kk = (int)(vk >> 16);
+  if (!valid_k(kk) || bs == 0 || bs > kMaxBlock) return fail(HUFB200_E_CORRUPT, "bad container parameters");
+  if (hufb200_blocks_count(rs, bs) != nb) return fail(HUFB200_E_CORRUPT, "block count does not match raw size");
+  if (n < kContainerHeader + 4 * (size_t)nb) return fail(HUFB200_E_CORRUPT, "truncated block index");
+  if (k) *k = kk;
+  if (block_size) *block_size = bs;
+  if (raw_size) *raw_size = rs;
+  if (n_blocks) *n_blocks = nb;
+  return HUFB200_OK;
+}
+
+int hufb200_decompress_blocks(const uint8_t* c, size_t n, uint8_t* out, size_t cap, size_t* out_len) {
+  int k = 0;
+  size_t bs = 0, rs = 0, nb = 0;
+  int rc = hufb200_container_info(c, n, &k, &bs, &rs, &nb);
+  if (rc) return rc;
+  if (!out_len) return fail(HUFB200_E_INVALID, "null pointer");
+  *out_len = rs;
+  if (rs > cap) return fail(HUFB200_E_NOSPACE, "need %zu bytes, have %zu", rs, cap);
+  if (nb == 0) return HUFB200_OK;
+  const uint8_t* index = c + kContainerHeader;
+  const uint8_t* payload = index + 4 * nb;
+  const size_t payload_n = n - kContainerHeader - 4 * nb;
+  uint64_t sum = 0;
+  for (size_t b = 0; b < nb; ++b) {
+    uint32_t s;
+    memcpy(&s, index + 4 * b, 4);
+    sum += s;
+  }
+  if (sum != payload_n) return fail(HUFB200_E_CORRUPT, "block sizes do not add up to the payload size");
+  Workspace& ws = g_ws;
+  CU(ws.in.reserve(payload_n + 32));
+  CU(ws.out.reserve(rs + 16));
+  CU(ws.sizes.reserve(4 * (nb + 1)));
+  CU(ws.offsets.reserve(8 * (nb + 1)));
+  CU(ws.misc.reserve(256));
+  CU(cudaMemcpyAsync(ws.in.p, payload, payload_n, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(ws.sizes.p, index, 4 * nb, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemsetAsync(ws.misc.p, 0, 4, 0));
+  CU(launch_scan_sizes(ws.sizes.as<uint32_t>(), (uint32_t)nb, ws.offsets.as<unsigned long long>(), nullptr, 0));
+  rc = hufb200_decompress_blocks_dev(k, bs, ws.in.as<uint8_t>(), ws.offsets.as<uint64_t>(),
+                                     ws.sizes.as<uint32_t>(), nb, ws.out.as<uint8_t>(), rs,
+                                     ws.misc.as<uint32_t>(), nullptr);
+  if (rc) return rc;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  uint32_t status = 0;
+  CU(cudaMemcpyAsync(&status, ws.misc.p, 4, cudaMemcpyDeviceToHost, 0));
+  CU(cudaMemcpyAsync(out, ws.out.p, rs, cudaMemcpyDeviceToHost, 0));
+  CU(cudaStreamSynchronize(0));
+  if (status) return fail(HUFB200_E_CORRUPT, "malformed block in container");
+  return HUFB200_OK;
+}
+
+/* ------------------------------------------------------------- device-resident */
+
+int hufb200_compress_blocks_dev(int k, size_t block_size, const uint8_t* d_raw, size_t n, uint8_t* d_out,
+                                size_t slot_stride, uint32_t* d_comp_sizes, const void* d_table,
+                                uint32_t* d_status, void* stream) {
+  if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
+  if (block_size == 0 || block_size > kMaxBlock) return fail(HUFB200_E_INVALID, "block_size outside 1..2^30");
+  if (block_size % 16 || ((uintptr_t)d_raw & 15) || ((uintptr_t)d_out & 15) || slot_stride % 16)
+    return fail(HUFB200_E_INVALID, "block_size, slot_stride, d_raw and d_out must be 16-byte aligned");
+  if (slot_stride < hufb200_slot_stride(block_size, k)) return fail(HUFB200_E_INVALID, "slot_stride too small");
+  const size_t nb = hufb200_blocks_count(n, block_size);
+  if (nb >> 31) return fail(HUFB200_E_INVALID, "too many blocks");
+  if (nb && (!d_raw || !d_out || !d_comp_sizes)) return fail(HUFB200_E_INVALID, "null pointer");
+  return do_compress_dev(k, block_size, d_raw, n, (uint32_t)nb, d_out, slot_stride, d_comp_sizes, d_table, 0,
+                         d_status, (cudaStream_t)stream);
+}
+
+int hufb200_decompress_blocks_dev(int k, size_t block_size, const uint8_t* d_comp, const uint64_t* d_offsets,
+                                  const uint32_t* d_comp_sizes, size_t n_blocks, uint8_t* d_raw, size_t raw_n,
+                                  uint32_t* d_status, void* stream) {
+  if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
+  if (block_size == 0 || block_size > kMaxBlock) return fail(HUFB200_E_INVALID, "block_size outside 1..2^30");
+  if (n_blocks >> 31) return fail(HUFB200_E_INVALID, "too many blocks");
+  if (hufb200_blocks_count(raw_n, block_size) != n_blocks)
+    return fail(HUFB200_E_INVALID, "n_blocks does not match raw_n / block_size");
+  if (n_blocks && (!d_comp || !d_offsets || !d_comp_sizes || !d_raw)) return fail(HUFB200_E_INVALID, "null pointer");
+  CU(launch_decompress(d_comp, reinterpret_cast<const unsigned long long*>(d_offsets), d_comp_sizes,
+                       (uint32_t)n_blocks, k, decode_bpc(k), d_raw, raw_n, (uint32_t)block_size, d_status,
+                       (cudaStream_t)stream));
+  if (n_blocks) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return HUFB200_OK;
+}
+
+int hufb200_pack_blocks_dev(const uint8_t* d_slots, size_t slot_stride, const uint32_t* d_comp_sizes,
+                            size_t n_blocks, uint8_t* d_packed, uint64_t* d_offsets, uint64_t* d_total,
+                            void* stream) {
+  if (n_blocks >> 31) return fail(HUFB200_E_INVALID, "too many blocks");
+  if (!d_offsets || (n_blocks && (!d_slots || !d_comp_sizes))) return fail(HUFB200_E_INVALID, "null pointer");
+  CU(launch_pack(d_slots, slot_stride, d_comp_sizes, (uint32_t)n_blocks, d_packed,
+                 reinterpret_cast<unsigned long long*>(d_offsets), reinterpret_cast<unsigned long long*>(d_total),
+                 (cudaStream_t)stream));
+  g_launches.fetch_add(n_blocks && d_packed ? 2 : 1, std::memory_order_relaxed);
+  return HUFB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,844 @@
+// huf_kernels.cu -- sm_100a kernels of the multi-stream Huffman hot path.
+//
+//   k_histogram          byte histogram, lane-privatised shared-memory bins, 128-bit loads
+//   k_build_table        canonical table from a 256 x u64 histogram (shared-table mode)
+//   k_make_table         same from a u32 histogram, dumping every field (ABI/table parity)
+//   k_compress_blocks    fused per-block histogram -> table -> stream lengths -> encode
+//   k_decompress_blocks  header parse -> two-symbol table -> one lane per stream decode
+//   k_dump_dtable        the decode kernel's table builder, for parity tests
+//   k_scan_sizes/k_pack  slot layout -> packed layout
+//
+// Reference behaviour: ahartik/huffman-avx512 codec/huffman.cpp, codec/histogram.cpp.
+#include "huf_device.cuh"
+#include "huf_kernels.h"
+
+namespace hufb200 {
+
+// ===========================================================================
+// Histogram (MakeHistogram, codec/histogram.cpp:193-201; 8 private tables there,
+// :18-20 -- here 32 lane-private columns so that no two lanes of a warp ever
+// touch the same bank or address, whatever the symbol distribution).
+// bins[sym * 32 + lane]
+// ===========================================================================
+__device__ __forceinline__ void bins_add_word(uint32_t* bins_lane, uint32_t w) {
+  atomicAdd(bins_lane + ((w & 0xffu) << 5), 1u);
+  atomicAdd(bins_lane + (((w >> 8) & 0xffu) << 5), 1u);
+  atomicAdd(bins_lane + (((w >> 16) & 0xffu) << 5), 1u);
+  atomicAdd(bins_lane + ((w >> 24) << 5), 1u);
+}
+__device__ __forceinline__ void bins_add_vec(uint32_t* bins_lane, const uint4& v) {
+  bins_add_word(bins_lane, v.x);
+  bins_add_word(bins_lane, v.y);
+  bins_add_word(bins_lane, v.z);
+  bins_add_word(bins_lane, v.w);
+}
+// column sum of bin `t`, rotated start so the 32 threads of a warp hit distinct banks
+__device__ __forceinline__ uint32_t bins_reduce(const uint32_t* bins, int t) {
+  uint32_t s = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) s += bins[(t << 5) + ((i + t) & 31)];
+  return s;
+}
+
+// Accumulates the bytes [p, p+n) into the CTA's lane-private bins (all threads).
+__device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p, uint64_t n) {
+  uint32_t* bl = bins + lane_id();
+  const uint64_t mis = (16 - ((uintptr_t)p & 15)) & 15;
+  const uint64_t head = mis < n ? mis : n;
+  for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) atomicAdd(bl + ((uint32_t)p[i] << 5), 1u);
+  const uint4* v = reinterpret_cast<const uint4*>(p + head);
+  const uint64_t nvec = (n - head) >> 4;
+  uint64_t i = threadIdx.x;
+  const uint64_t step = blockDim.x;
+  for (; i + 3 * step < nvec; i += 4 * step) {  // 4 loads in flight per thread
+    const uint4 a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
+    bins_add_vec(bl, a);
+    bins_add_vec(bl, b);
+    bins_add_vec(bl, c);
+    bins_add_vec(bl, d);
+  }
+  for (; i < nvec; i += step) bins_add_vec(bl, v[i]);
+  const uint64_t done = head + (nvec << 4);
+  for (uint64_t j = done + threadIdx.x; j < n; j += blockDim.x) atomicAdd(bl + ((uint32_t)p[j] << 5), 1u);
+}
+
+__global__ void __launch_bounds__(kHistThreads)
+k_histogram(const uint8_t* __restrict__ in, uint64_t n, unsigned long long* __restrict__ out) {
+  __shared__ uint32_t bins[256 * 32];
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  // contiguous 16-byte-granular share per CTA
+  const uint64_t nvec_total = (n + 15) >> 4;
+  const uint64_t per = (nvec_total + gridDim.x - 1) / gridDim.x;
+  const uint64_t beg = (uint64_t)blockIdx.x * per * 16;
+  if (beg < n) {
+    uint64_t len = per * 16;
+    if (beg + len > n) len = n - beg;
+    // 32-bit lane counters: a CTA's share is processed in pieces of < 2^32 bytes
+    bins_accumulate(bins, in + beg, len);
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    const uint32_t s = bins_reduce(bins, threadIdx.x);
+    if (s) atomicAdd(out + threadIdx.x, (unsigned long long)s);
+  }
+}
+
+// ===========================================================================
+// Table kernels
+// ===========================================================================
+__global__ void __launch_bounds__(32) k_build_table(const unsigned long long* __restrict__ hist,
+                                                    HufTable* __restrict__ out) {
+  __shared__ HufTable tab;
+  __shared__ TableScratch sc;
+  __shared__ unsigned long long h[256];
+  for (int i = threadIdx.x; i < 256; i += 32) h[i] = hist[i];
+  __syncwarp();
+  build_table_warp<unsigned long long>(h, &tab, &sc);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&tab);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out);
+  for (int i = threadIdx.x; i < (int)(sizeof(HufTable) / 4); i += 32) dst[i] = src[i];
+}
+
+// mode 0: build from hist (u32). mode 1: build from (len_count, syms).
+__global__ void __launch_bounds__(32) k_make_table(const uint32_t* __restrict__ hist,
+                                                   const uint16_t* __restrict__ in_len_count,
+                                                   const uint8_t* __restrict__ in_syms, int in_n,
+                                                   int mode, HufTable* __restrict__ out) {
+  __shared__ HufTable tab;
+  __shared__ TableScratch sc;
+  __shared__ uint32_t h[256];
+  __shared__ uint16_t lc[16];
+  __shared__ uint8_t sy[256];
+  if (mode == 0) {
+    for (int i = threadIdx.x; i < 256; i += 32) h[i] = hist[i];
+    __syncwarp();
+    build_table_warp<uint32_t>(h, &tab, &sc);
+  } else {
+    for (int i = threadIdx.x; i < 13; i += 32) lc[i] = in_len_count[i];
+    for (int i = threadIdx.x; i < in_n; i += 32) sy[i] = in_syms[i];
+    __syncwarp();
+    table_from_lengths_warp(lc, sy, in_n, &tab, &sc);
+  }
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&tab);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out);
+  for (int i = threadIdx.x; i < (int)(sizeof(HufTable) / 4); i += 32) dst[i] = src[i];
+}
+
+// ===========================================================================
+// Fused compress kernel: one CTA per block (CompressMulti<K>, codec/huffman.cpp:738-846)
+// ===========================================================================
+constexpr int kRingWords = 256;  // per-warp staging ring, in 32-bit stream words
+
+struct CompSmem {
+  union {
+    uint32_t bins[256 * 32];                  // histogram phase
+    uint32_t ring[kCompWarps][kRingWords];    // encode phase
+  } u;
+  uint32_t hist[256];
+  HufTable tab;
+  TableScratch sc;
+  unsigned long long stream_bits[kMaxK];
+  uint32_t region_end[kMaxK];  // cumulative end offsets relative to the payload start (:772-786)
+  uint32_t bad;
+};
+
+__device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) {  // shift >= 32 gives 0
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+  return r;
+}
+__device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t s) {
+  uint32_t r;
+  asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+  return r;
+}
+
+// Loads the 16 symbols [off, off+16) of a slice as four little-endian words; symbols
+// beyond `valid` read as 0 and are masked by the caller.
+__device__ __forceinline__ uint4 load16(const uint8_t* sp, uint32_t off, uint32_t valid, bool aligned) {
+  if (aligned && valid >= 16) return *reinterpret_cast<const uint4*>(sp + off);
+  uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if ((uint32_t)i < valid) w[i >> 2] |= (uint32_t)sp[off + i] << (8 * (i & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Sum of code lengths of the (up to) 4 symbols in w; `valid` symbols count.
+__device__ __forceinline__ uint32_t word_len(const uint32_t* enc, uint32_t w) {
+  return (enc[w & 0xffu] >> 16) + (enc[(w >> 8) & 0xffu] >> 16) + (enc[(w >> 16) & 0xffu] >> 16) +
+         (enc[w >> 24] >> 16);
+}
+
+// Per-stream bit total (the reference derives it from per-stream histograms, :776-782).
+__device__ inline unsigned long long stream_length_warp(const uint32_t* enc, const uint8_t* sp,
+                                                        uint32_t sz, uint32_t* bad) {
+  const int lane = lane_id();
+  const bool aligned = (((uintptr_t)sp) & 15) == 0;
+  unsigned long long acc = 0;
+  uint32_t flag = 0;
+  const uint32_t full = sz & ~511u;
+  for (uint32_t base = 0; base < full; base += 512) {
+    const uint4 v = load16(sp, base + lane * 16, 16, aligned);
+    const uint32_t l = word_len(enc, v.x) + word_len(enc, v.y) + word_len(enc, v.z) + word_len(enc, v.w);
+    flag |= l;
+    acc += l;
+  }
+  if (full < sz) {
+    const uint32_t off = full + lane * 16;
+    const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
+    for (uint32_t i = 0; i < valid; ++i) {
+      const uint32_t l = enc[sp[off + i]] >> 16;
+      flag |= l;
+      acc += l;
+    }
+  }
+  if (flag & 0x7fffc000u) atomicOr(bad, 1u);  // a symbol without a code (kEncInvalid)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  return acc;
+}
+
+// ORs the `len` low bits of `code` (len <= 24) into the ring at stream bit position `pos`.
+__device__ __forceinline__ void ring_put(uint32_t* ring, uint32_t pos, uint32_t code, uint32_t len) {
+  const uint32_t t = shl_c(code, 32u - len);  // left-aligned; len == 0 gives 0
+  const uint32_t o = pos & 31u;
+  const uint32_t w = (pos >> 5) & (kRingWords - 1);
+  atomicOr(ring + w, t >> o);
+  atomicOr(ring + ((w + 1) & (kRingWords - 1)), shl_c(t, 32u - o));
+}
+
+// Two table entries -> (code, len) of the pair, first symbol in the high bits.
+__device__ __forceinline__ void pair_code(uint32_t e0, uint32_t e1, uint32_t& code, uint32_t& len) {
+  const uint32_t l1 = e1 >> 16;
+  code = ((e0 & 0xffffu) << l1) | (e1 & 0xffffu);
+  len = (e0 >> 16) + l1;
+}
+
+// Encodes one stream (slice sp[0..sz)) whose region ends at byte offset e_off of dst and is
+// `region` bytes long (CodeWriter semantics, codec/huffman.cpp:439-500: MSB-first bitstream
+// whose first byte is the region's LAST byte; the first 8 bytes of the region stay zero).
+//
+// Stream word q (32 stream bits, MSB first) occupies bytes e_off-4q-4 .. e_off-4q-1 as a
+// little-endian u32.  With r = e_off & 3 the aligned output word number m at dst + (e_off-r) - 4m
+// equals funnelshift_l(W[m], W[m-1], 8r) (W[-1] = 0), so the warp emits aligned 128-byte rows.
+__device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t* ring, const uint8_t* sp,
+                                          uint32_t sz, unsigned long long bits, uint8_t* dst,
+                                          uint32_t e_off, uint32_t region) {
+  const int lane = lane_id();
+  const bool aligned = (((uintptr_t)sp) & 15) == 0;
+  const uint32_t r = e_off & 3u;
+  const uint32_t e_al = e_off - r;
+  const uint32_t s_off = e_off - region;
+  const uint32_t s_al = (s_off + 3u) & ~3u;
+  const uint32_t m_first = r ? 0u : 1u;
+  const uint32_t m_last = (e_al - s_al) >> 2;  // inclusive
+  uint32_t* out_words = reinterpret_cast<uint32_t*>(dst + e_al);  // word m at out_words[-m]
+
+  unsigned long long bitpos = 0;
+  uint32_t m_next = m_first;
+  for (uint32_t base = 0; base < sz; base += 512) {
+    const uint32_t off = base + lane * 16;
+    const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
+    const uint4 v = load16(sp, off, valid, aligned);
+    uint32_t code[8], len[8];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (valid == 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        pair_code(enc[w[j] & 0xffu], enc[(w[j] >> 8) & 0xffu], code[2 * j], len[2 * j]);
+        pair_code(enc[(w[j] >> 16) & 0xffu], enc[w[j] >> 24], code[2 * j + 1], len[2 * j + 1]);
+      }
+    } else {  // last iteration of the slice: symbols past its end contribute no bits
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const uint32_t b0 = (w[p >> 1] >> (16 * (p & 1))) & 0xffu;
+        const uint32_t b1 = (w[p >> 1] >> (16 * (p & 1) + 8)) & 0xffu;
+        const uint32_t e0 = (uint32_t)(2 * p) < valid ? enc[b0] : 0u;
+        const uint32_t e1 = (uint32_t)(2 * p + 1) < valid ? enc[b1] : 0u;
+        pair_code(e0, e1, code[p], len[p]);
+      }
+    }
+    uint32_t lane_len = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) lane_len += len[p];
+    const uint32_t incl = warp_incl_scan(lane_len);
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t pos = (uint32_t)(bitpos & 0xffffffffu) + (incl - lane_len);  // only low bits matter
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      ring_put(ring, pos, code[p], len[p]);
+      pos += len[p];
+    }
+    bitpos += total;
+    __syncwarp();
+    // flush the complete stream words
+    const uint32_t wc = (uint32_t)(bitpos >> 5);
+    for (uint32_t m = m_next + lane; m < wc; m += 32) {
+      const uint32_t hi = m ? ring[(m - 1) & (kRingWords - 1)] : 0u;
+      const uint32_t lo = ring[m & (kRingWords - 1)];
+      out_words[-(long)m] = __funnelshift_l(lo, hi, 8 * r);
+    }
+    __syncwarp();
+    if (wc > m_next) {
+      for (uint32_t j = (m_next ? m_next - 1 : 0u) + lane; j + 1 < wc; j += 32) ring[j & (kRingWords - 1)] = 0;
+      m_next = wc;
+    }
+    __syncwarp();
+  }
+  // tail: partial word, padding and the zero slop below the stream
+  const uint32_t wtot = (uint32_t)((bits + 31) >> 5);
+  for (uint32_t m = m_next + lane; m <= m_last; m += 32) {
+    const uint32_t hi = (m >= 1 && m - 1 < wtot) ? ring[(m - 1) & (kRingWords - 1)] : 0u;
+    const uint32_t lo = (m < wtot) ? ring[m & (kRingWords - 1)] : 0u;
+    out_words[-(long)m] = __funnelshift_l(lo, hi, 8 * r);
+  }
+  __syncwarp();
+  for (int j = lane; j < kRingWords; j += 32) ring[j] = 0;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kCompThreads)
+k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_size, int K,
+                  uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
+                  uint32_t* __restrict__ comp_sizes, const HufTable* __restrict__ shared_tab,
+                  int check_presence, uint32_t* __restrict__ status) {
+  __shared__ CompSmem sm;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    const uint64_t boff = (uint64_t)b * block_size;
+    const uint8_t* src = raw + boff;
+    const uint32_t bn = (uint32_t)((n - boff) < (uint64_t)block_size ? (n - boff) : (uint64_t)block_size);
+    uint8_t* dst = out + (uint64_t)b * slot_stride;
+    if (tid == 0) sm.bad = 0;
+
+    // ---- phase 1: histogram (skipped in shared-table mode unless presence is checked)
+    const bool need_hist = (shared_tab == nullptr) || check_presence;
+    if (need_hist) {
+      uint4* z = reinterpret_cast<uint4*>(sm.u.bins);
+      for (int i = tid; i < 256 * 32 / 4; i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      bins_accumulate(sm.u.bins, src, bn);
+      __syncthreads();
+      if (tid < 256) sm.hist[tid] = bins_reduce(sm.u.bins, tid);
+      __syncthreads();
+    }
+    // ---- phase 2: table (warp 0) while the other warps clear the staging rings
+    if (shared_tab != nullptr) {
+      const uint32_t* s = reinterpret_cast<const uint32_t*>(shared_tab);
+      uint32_t* d = reinterpret_cast<uint32_t*>(&sm.tab);
+      for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += kCompThreads) d[i] = s[i];
+    } else if (warp == 0) {
+      build_table_warp<uint32_t>(sm.hist, &sm.tab, &sm.sc);
+    }
+    {
+      uint32_t* rz = &sm.u.ring[0][0];
+      for (int i = tid; i < kCompWarps * kRingWords; i += kCompThreads) rz[i] = 0;
+    }
+    __syncthreads();
+    if (shared_tab != nullptr && check_presence && tid < 256) {
+      if (sm.hist[tid] != 0 && sm.tab.enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
+    }
+
+    // ---- phase 3: header prefix (:799-808) and per-stream bit totals (:772-782)
+    const uint32_t hdr = sm.tab.hdr_len;
+    const uint32_t mask = sm.tab.len_mask;
+    const uint32_t npop = (uint32_t)__popc(mask);
+    for (uint32_t i = tid; i < hdr; i += kCompThreads) {
+      uint8_t v;
+      if (i < 4) v = (uint8_t)(bn >> (8 * i));
+      else if (i < 8) v = (uint8_t)(mask >> (8 * (i - 4)));
+      else if (i < 8 + npop) {
+        int bit = 0;  // position of the (i-8)-th set bit of the mask
+        for (uint32_t seen = 0;; ++bit)
+          if ((mask >> bit) & 1u) {
+            if (seen == i - 8) break;
+            ++seen;
+          }
+        v = (uint8_t)sm.tab.len_count[bit];                // 256 wraps to 0 (:804)
+      } else v = sm.tab.sorted_syms[i - 8 - npop];
+      dst[i] = v;
+    }
+    for (int s = warp; s < K; s += kCompWarps) {
+      uint32_t st, sz;
+      slice_geom(bn, K, s, st, sz);
+      const unsigned long long bits = stream_length_warp(sm.tab.enc, src + st, sz, &sm.bad);
+      if (lane == 0) sm.stream_bits[s] = bits;
+    }
+    __syncthreads();
+    const bool bad = sm.bad != 0;
+    // ---- phase 4: region offsets and the end_offset table (:783-786, :809-811)
+    if (tid == 0) {
+      uint32_t pos = 0;
+      for (int s = 0; s < K; ++s) {
+        pos += (uint32_t)((sm.stream_bits[s] + 7) >> 3) + kSlop;
+        sm.region_end[s] = pos;
+      }
+    }
+    __syncthreads();
+    const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
+    if (bad) {
+      if (tid == 0) {
+        comp_sizes[b] = 0;
+        if (status) atomicOr(status, 1u);
+      }
+      __syncthreads();
+      continue;
+    }
+    for (int s = tid; s < K - 1; s += kCompThreads) {
+      const uint32_t e = sm.region_end[s];
+      uint8_t* p = dst + hdr + 4 * s;
+      p[0] = (uint8_t)e;
+      p[1] = (uint8_t)(e >> 8);
+      p[2] = (uint8_t)(e >> 16);
+      p[3] = (uint8_t)(e >> 24);
+    }
+    if (tid == 0) {
+      // slop bytes of region 0 that share an aligned word with the header
+      for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;
+      comp_sizes[b] = hdr_total + sm.region_end[K - 1];
+    }
+    // ---- phase 5: encode, one warp per stream
+    for (int s = warp; s < K; s += kCompWarps) {
+      uint32_t st, sz;
+      slice_geom(bn, K, s, st, sz);
+      const uint32_t e_off = hdr_total + sm.region_end[s];
+      const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
+      encode_stream_warp(sm.tab.enc, sm.u.ring[warp], src + st, sz, sm.stream_bits[s], dst, e_off, region);
+    }
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// Decompress kernel: one lane per stream (DecompressMultiImpl<K, Decoder2x>,
+// codec/huffman.cpp:892-955; ParseCompressedHeader :714-736; Decoder2x :642-704)
+// ===========================================================================
+struct DecBlockInfo {
+  uint32_t ok;
+  uint32_t raw_size;
+  uint32_t comp_size;
+  uint32_t payload_off;  // header bytes incl. the end_offset table
+  uint32_t ends_off;     // offset of the end_offset table
+  uint32_t syms_off;
+  uint32_t num_syms;
+  uint32_t code_end[16];   // left-aligned (12-bit) end of the code range of each length
+  uint32_t first_idx[16];  // index into sorted_syms of the first code of each length
+};
+
+// Table entry: byte0 = bits consumed, byte1 = sym0, byte2 = sym1, byte3 = num_syms | len(sym0)<<4
+// (DecodedSym2x, :634-640, plus the first code's own length in the spare nibble).
+__device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, int tid,
+                                    int nthreads) {
+  for (int e = tid; e < 4096; e += nthreads) {
+    int l = 0;
+    while (l <= kMaxCodeLen && (uint32_t)e >= bi->code_end[l]) ++l;
+    uint32_t ent;
+    if (l > kMaxCodeLen) {
+      ent = 12u | (1u << 24) | (12u << 28);  // not covered by any code (malformed table)
+    } else {
+      const uint32_t lo = l ? bi->code_end[l - 1] : 0u;
+      const uint32_t idx = bi->first_idx[l] + (((uint32_t)e - lo) >> (kMaxCodeLen - l));
+      const uint32_t sym = idx < bi->num_syms ? syms[idx] : 0u;
+      ent = (uint32_t)l | (sym << 8) | (1u << 24) | ((uint32_t)l << 28);
+    }
+    T[e] = ent;
+  }
+  __syncthreads();
+  for (int e = tid; e < 4096; e += nthreads) {
+    const uint32_t e1 = T[e];
+    const uint32_t l1 = e1 >> 28;
+    const uint32_t rest = ((uint32_t)e << l1) & 0xfffu;
+    const uint32_t e2 = T[rest];
+    const uint32_t l2 = e2 >> 28;
+    if (l1 + l2 <= (uint32_t)kMaxCodeLen)  // :653
+      T[e] = (l1 + l2) | (e1 & 0xff00u) | ((e2 & 0xff00u) << 8) | (2u << 24) | (l1 << 28);
+  }
+  __syncthreads();
+}
+
+__device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
+                                    DecBlockInfo* bi) {
+  bi->ok = 0;
+  bi->comp_size = comp_size;
+  if (comp_size < 8u + 4u * (uint32_t)(K - 1)) return;
+  uint32_t raw_size = 0, mask = 0;
+  for (int i = 0; i < 4; ++i) {
+    raw_size |= (uint32_t)blk[i] << (8 * i);
+    mask |= (uint32_t)blk[4 + i] << (8 * i);
+  }
+  bi->raw_size = raw_size;
+  if (mask >> (kMaxCodeLen + 1)) return;
+  if (raw_size != expect_raw) return;
+  const uint32_t npop = (uint32_t)__popc(mask);
+  if (8u + npop > comp_size) return;
+  uint32_t pos = 8, nsyms = 0, code = 0;
+  for (int l = 0; l <= kMaxCodeLen; ++l) {
+    uint32_t cnt = 0;
+    if (mask & (1u << l)) {
+      cnt = blk[pos++];
+      if (npop == 1 && cnt == 0) cnt = 256;  // :724-728
+    }
+    bi->first_idx[l] = nsyms;
+    nsyms += cnt;
+    code += cnt << (kMaxCodeLen - l);
+    bi->code_end[l] = code;
+  }
+  if (nsyms > 256) return;
+  if (raw_size != 0 && nsyms == 0) return;
+  bi->num_syms = nsyms;
+  bi->syms_off = pos;
+  bi->ends_off = pos + nsyms;
+  bi->payload_off = pos + nsyms + 4u * (uint32_t)(K - 1);
+  if (bi->payload_off > comp_size) return;
+  bi->ok = 1;
+}
+
+__device__ __forceinline__ uint4 ld_chunk(uintptr_t addr, uintptr_t lo_lim) {
+  if (addr >= lo_lim) return *reinterpret_cast<const uint4*>(addr);
+  return make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(kDecMaxThreads)
+k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* __restrict__ offsets,
+                    const uint32_t* __restrict__ comp_sizes, uint32_t n_blocks, int K, int bpc,
+                    uint8_t* __restrict__ raw, uint64_t raw_n, uint32_t block_size,
+                    uint32_t* __restrict__ status) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  // layout: tables [bpc][4096] u32 | rings [nwarps][16][32] u32 | rows [nthreads][20] u8 | infos [bpc]
+  const int nthreads = blockDim.x;
+  const int nwarps = nthreads >> 5;
+  uint32_t* tables = reinterpret_cast<uint32_t*>(dsm);
+  uint32_t* rings = tables + (size_t)bpc * 4096;
+  uint8_t* rows = reinterpret_cast<uint8_t*>(rings + (size_t)nwarps * 16 * 32);
+  DecBlockInfo* infos = reinterpret_cast<DecBlockInfo*>(rows + (((size_t)nthreads * 20 + 15) & ~(size_t)15));
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const uint32_t b0 = blockIdx.x * (uint32_t)bpc;
+
+  // ---- header parse, one thread per block
+  if (tid < bpc) {
+    const uint32_t b = b0 + tid;
+    DecBlockInfo* bi = &infos[tid];
+    bi->ok = 0;
+    if (b < n_blocks) {
+      const uint64_t roff = (uint64_t)b * block_size;
+      const uint32_t expect = (uint32_t)((raw_n - roff) < (uint64_t)block_size ? (raw_n - roff) : (uint64_t)block_size);
+      parse_header(comp + offsets[b], comp_sizes[b], K, expect, bi);
+      if (!bi->ok && status) atomicOr(status, 1u);
+    }
+  }
+  __syncthreads();
+  // ---- two-symbol tables
+  for (int lb = 0; lb < bpc; ++lb) {
+    const DecBlockInfo* bi = &infos[lb];
+    if (b0 + lb < n_blocks && bi->ok && bi->raw_size != 0) {
+      build_dtable(bi, comp + offsets[b0 + lb] + bi->syms_off, tables + (size_t)lb * 4096, tid, nthreads);
+    }
+  }
+  __syncthreads();
+
+  // ---- decode: thread t <-> (local block t / K, stream t % K)
+  const int lb = tid / K;
+  const int s = tid - lb * K;
+  const uint32_t b = b0 + (uint32_t)lb;
+  bool active = (lb < bpc) && (b < n_blocks);
+  const DecBlockInfo* bi = &infos[active ? lb : 0];
+  active = active && bi->ok && bi->raw_size != 0;
+
+  uint32_t left = 0;           // symbols still to produce
+  uint8_t* outp = nullptr;     // next output byte
+  uintptr_t e16 = 16, lo_lim = 0;
+  uint32_t used = 0;           // bits consumed from hi
+  uint32_t rd = 0, staged = 0, cidx = 0;
+  bool bad_lane = false;
+  if (active) {
+    const uint8_t* blk = comp + offsets[b];
+    uint32_t st, sz;
+    slice_geom(bi->raw_size, K, s, st, sz);
+    uint32_t e_off;
+    const uint32_t payload = bi->comp_size - bi->payload_off;
+    if (s == K - 1) e_off = payload;  // :901
+    else {
+      const uint8_t* p = blk + bi->ends_off + 4 * s;
+      e_off = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+    if (e_off > payload) {
+      bad_lane = true;
+      sz = 0;
+    }
+    left = sz;
+    outp = raw + (uint64_t)b * block_size + st;
+    const uintptr_t end_addr = (uintptr_t)(blk + bi->payload_off) + e_off;  // exclusive
+    e16 = (end_addr + 15) & ~(uintptr_t)15;
+    const uint32_t pad = (uint32_t)(e16 - end_addr);
+    lo_lim = (uintptr_t)blk & ~(uintptr_t)15;
+    rd = pad >> 2;
+    used = 8 * (pad & 3);
+  }
+  if (bad_lane && status) atomicOr(status, 1u);
+
+  const uint32_t* T = tables + (size_t)(lb < bpc ? lb : 0) * 4096;
+  uint32_t* col = rings + (size_t)warp * 16 * 32 + lane;  // word i at col[(i & 15) * 32]
+  uint8_t* row = rows + (size_t)tid * 20;
+
+  // prime: stage 3 chunks (12 words), keep two more in registers
+  uint4 p0, p1;
+  {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint4 ch = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
+      col[((staged + 0) & 15) * 32] = ch.w;
+      col[((staged + 1) & 15) * 32] = ch.z;
+      col[((staged + 2) & 15) * 32] = ch.y;
+      col[((staged + 3) & 15) * 32] = ch.x;
+      staged += 4;
+      ++cidx;
+    }
+    p0 = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
+    p1 = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 2), lo_lim) : make_uint4(0, 0, 0, 0);
+    cidx += 2;
+  }
+  uint32_t hi = col[(rd & 15) * 32];
+  uint32_t lo = col[((rd + 1) & 15) * 32];
+  uint32_t nx = col[((rd + 2) & 15) * 32];
+  rd += 3;
+
+  uint32_t cnt = 0;  // symbols already sitting in row[] (0 or 1 carried over)
+  const uint32_t max_left = __reduce_max_sync(0xffffffffu, left);
+  for (uint32_t round = 0; round * 16 < max_left; ++round) {
+    // top up the ring: a round consumes at most 7 words
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (staged - rd < 8) {
+        col[((staged + 0) & 15) * 32] = p0.w;
+        col[((staged + 1) & 15) * 32] = p0.z;
+        col[((staged + 2) & 15) * 32] = p0.y;
+        col[((staged + 3) & 15) * 32] = p0.x;
+        staged += 4;
+        p0 = p1;
+        p1 = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
+        ++cidx;
+      }
+    }
+    const uint32_t target = left < 16 ? left : 16;
+    while (cnt < target) {
+      const uint32_t code = __funnelshift_l(lo, hi, used) >> 20;
+      const uint32_t e = T[code];
+      used += e & 0xffu;
+      row[cnt] = (uint8_t)(e >> 8);
+      row[cnt + 1] = (uint8_t)(e >> 16);
+      cnt += (e >> 24) & 3u;
+      if (used >= 32) {
+        hi = lo;
+        lo = nx;
+        nx = col[(rd & 15) * 32];
+        ++rd;
+        used -= 32;
+      }
+    }
+    if (target) {
+      if (target == 16 && (((uintptr_t)outp) & 15) == 0) {
+        uint4 v;
+        v.x = *reinterpret_cast<const uint32_t*>(row + 0);
+        v.y = *reinterpret_cast<const uint32_t*>(row + 4);
+        v.z = *reinterpret_cast<const uint32_t*>(row + 8);
+        v.w = *reinterpret_cast<const uint32_t*>(row + 12);
+        *reinterpret_cast<uint4*>(outp) = v;
+      } else {
+        for (uint32_t i = 0; i < target; ++i) outp[i] = row[i];
+      }
+      outp += target;
+      left -= target;
+      if (cnt > target) {  // second symbol of the last pair belongs to the next round
+        row[0] = row[target];
+        cnt = 1;
+      } else {
+        cnt = 0;
+      }
+    }
+  }
+}
+
+// Dumps the decode kernel's two-symbol table in the reference's DecodedSym2x layout.
+__global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict__ len_count,
+                                                     const uint8_t* __restrict__ syms, int num_syms,
+                                                     uint8_t* __restrict__ out) {
+  __shared__ uint32_t T[4096];
+  __shared__ DecBlockInfo bi;
+  __shared__ uint8_t sy[256];
+  if (threadIdx.x == 0) {
+    uint32_t nsyms = 0, code = 0;
+    for (int l = 0; l <= kMaxCodeLen; ++l) {
+      bi.first_idx[l] = nsyms;
+      nsyms += len_count[l];
+      code += (uint32_t)len_count[l] << (kMaxCodeLen - l);
+      bi.code_end[l] = code;
+    }
+    bi.num_syms = (uint32_t)num_syms;
+  }
+  for (int i = threadIdx.x; i < num_syms; i += blockDim.x) sy[i] = syms[i];
+  __syncthreads();
+  build_dtable(&bi, sy, T, threadIdx.x, blockDim.x);
+  for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
+    const uint32_t v = T[e];
+    out[4 * e + 0] = (uint8_t)v;
+    out[4 * e + 1] = (uint8_t)(v >> 8);
+    out[4 * e + 2] = (uint8_t)(v >> 16);
+    out[4 * e + 3] = (uint8_t)((v >> 24) & 0xfu);
+  }
+}
+
+// ===========================================================================
+// Slot layout -> packed layout
+// ===========================================================================
+__global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict__ sizes, uint32_t n,
+                                                     unsigned long long* __restrict__ offsets,
+                                                     unsigned long long* __restrict__ total) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    unsigned long long v = i < n ? sizes[i] : 0ull;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += warp_sums[w];
+    const unsigned long long c = carry;
+    if (i < n) offsets[i] = c + woff + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + woff + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ slots, uint64_t slot_stride,
+                                              const uint32_t* __restrict__ sizes,
+                                              const unsigned long long* __restrict__ offsets,
+                                              uint8_t* __restrict__ packed) {
+  const uint32_t b = blockIdx.x;
+  const uint8_t* src = slots + (uint64_t)b * slot_stride;
+  uint8_t* dst = packed + offsets[b];
+  const uint32_t sz = sizes[b];
+  // destination-aligned 16-byte stores, byte-granular edges
+  const uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+  const uint32_t h = head < sz ? head : sz;
+  for (uint32_t i = threadIdx.x; i < h; i += blockDim.x) dst[i] = src[i];
+  const uint32_t nvec = (sz - h) >> 4;
+  for (uint32_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint8_t* s = src + h + 16 * v;
+    uint32_t w[4];
+    if ((h & 3) == 0) {
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s);
+      w[0] = s32[0]; w[1] = s32[1]; w[2] = s32[2]; w[3] = s32[3];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        w[j] = (uint32_t)s[4 * j] | ((uint32_t)s[4 * j + 1] << 8) | ((uint32_t)s[4 * j + 2] << 16) |
+               ((uint32_t)s[4 * j + 3] << 24);
+    }
+    *reinterpret_cast<uint4*>(dst + h + 16 * v) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (uint32_t i = h + 16 * nvec + threadIdx.x; i < sz; i += blockDim.x) dst[i] = src[i];
+}
+
+// ===========================================================================
+// Launchers (called from huf_api.cu)
+// ===========================================================================
+size_t table_bytes() { return sizeof(HufTable); }
+
+cudaError_t launch_histogram(const uint8_t* d_in, uint64_t n, unsigned long long* d_out, int grid,
+                             cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(d_out, 0, 256 * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  if (n == 0) return cudaSuccess;
+  k_histogram<<<grid, kHistThreads, 0, st>>>(d_in, n, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_build_table(const unsigned long long* d_hist, void* d_table, cudaStream_t st) {
+  k_build_table<<<1, 32, 0, st>>>(d_hist, reinterpret_cast<HufTable*>(d_table));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_make_table(const uint32_t* d_hist, const uint16_t* d_len_count, const uint8_t* d_syms,
+                              int n, int mode, void* d_table, cudaStream_t st) {
+  k_make_table<<<1, 32, 0, st>>>(d_hist, d_len_count, d_syms, n, mode, reinterpret_cast<HufTable*>(d_table));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_size, int K, uint32_t n_blocks,
+                            uint8_t* d_out, uint64_t slot_stride, uint32_t* d_sizes, const void* d_table,
+                            int check_presence, uint32_t* d_status, int grid, cudaStream_t st) {
+  if (n_blocks == 0) return cudaSuccess;
+  k_compress_blocks<<<grid, kCompThreads, 0, st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride,
+                                                   d_sizes, reinterpret_cast<const HufTable*>(d_table),
+                                                   check_presence, d_status);
+  return cudaGetLastError();
+}
+
+size_t decompress_smem_bytes(int K, int bpc) {
+  const int nthreads = ((K * bpc + 31) / 32) * 32;
+  const int nwarps = nthreads / 32;
+  size_t b = (size_t)bpc * 4096 * 4 + (size_t)nwarps * 16 * 32 * 4;
+  b += ((size_t)nthreads * 20 + 15) & ~(size_t)15;
+  b += (size_t)bpc * sizeof(DecBlockInfo);
+  return b;
+}
+
+cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
+                              const uint32_t* d_sizes, uint32_t n_blocks, int K, int bpc, uint8_t* d_raw,
+                              uint64_t raw_n, uint32_t block_size, uint32_t* d_status, cudaStream_t st) {
+  if (n_blocks == 0) return cudaSuccess;
+  const int nthreads = ((K * bpc + 31) / 32) * 32;
+  const size_t smem = decompress_smem_bytes(K, bpc);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_decompress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const uint32_t grid = (n_blocks + bpc - 1) / bpc;
+  k_decompress_blocks<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n,
+                                                    block_size, d_status);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dump_dtable(const uint16_t* d_len_count, const uint8_t* d_syms, int num_syms, uint8_t* d_out,
+                               cudaStream_t st) {
+  k_dump_dtable<<<1, 256, 0, st>>>(d_len_count, d_syms, num_syms, d_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes, uint32_t n_blocks,
+                        uint8_t* d_packed, unsigned long long* d_offsets, unsigned long long* d_total,
+                        cudaStream_t st) {
+  k_scan_sizes<<<1, 1024, 0, st>>>(d_sizes, n_blocks, d_offsets, d_total);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || n_blocks == 0 || d_packed == nullptr) return e;
+  k_pack<<<n_blocks, 256, 0, st>>>(d_slots, slot_stride, d_sizes, d_offsets, d_packed);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_sizes(const uint32_t* d_sizes, uint32_t n_blocks, unsigned long long* d_offsets,
+                              unsigned long long* d_total, cudaStream_t st) {
+  k_scan_sizes<<<1, 1024, 0, st>>>(d_sizes, n_blocks, d_offsets, d_total);
+  return cudaGetLastError();
+}
+
+}  // namespace hufb200

@@ -1,0 +1,36 @@
+// huf_kernels.h -- launcher interface between huf_kernels.cu and huf_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace hufb200 {
+
+constexpr int kHistThreads = 512;
+constexpr int kCompThreads = 512;
+constexpr int kCompWarps = kCompThreads / 32;
+constexpr int kDecMaxThreads = 256;
+
+size_t table_bytes();
+size_t decompress_smem_bytes(int K, int bpc);
+
+cudaError_t launch_histogram(const uint8_t* d_in, uint64_t n, unsigned long long* d_out, int grid,
+                             cudaStream_t st);
+cudaError_t launch_build_table(const unsigned long long* d_hist, void* d_table, cudaStream_t st);
+cudaError_t launch_make_table(const uint32_t* d_hist, const uint16_t* d_len_count, const uint8_t* d_syms,
+                              int n, int mode, void* d_table, cudaStream_t st);
+cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_size, int K, uint32_t n_blocks,
+                            uint8_t* d_out, uint64_t slot_stride, uint32_t* d_sizes, const void* d_table,
+                            int check_presence, uint32_t* d_status, int grid, cudaStream_t st);
+cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
+                              const uint32_t* d_sizes, uint32_t n_blocks, int K, int bpc, uint8_t* d_raw,
+                              uint64_t raw_n, uint32_t block_size, uint32_t* d_status, cudaStream_t st);
+cudaError_t launch_dump_dtable(const uint16_t* d_len_count, const uint8_t* d_syms, int num_syms, uint8_t* d_out,
+                               cudaStream_t st);
+cudaError_t launch_pack(const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes, uint32_t n_blocks,
+                        uint8_t* d_packed, unsigned long long* d_offsets, unsigned long long* d_total,
+                        cudaStream_t st);
+cudaError_t launch_scan_sizes(const uint32_t* d_sizes, uint32_t n_blocks, unsigned long long* d_offsets,
+                              unsigned long long* d_total, cudaStream_t st);
+
+}  // namespace hufb200

@@ -1,0 +1,99 @@
+"""Device-resident API (what bench.py times): torch tensors in HBM, kernels on torch's stream."""
+import numpy as np
+import pytest
+
+from _cases import biased, english
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(data):
+    import torch
+    return torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+
+
+@pytest.mark.parametrize("k,bs", [(32, 131072), (4, 16384), (8, 65536), (16, 32768), (48, 131072), (32, 1 << 20)])
+def test_blocks_dev_parity_and_roundtrip(huf, oracle, k, bs):
+    import torch
+    n = 3 * bs + bs // 2 + 16  # ragged last block
+    data = biased(n, seed=k + bs)
+    codec = huf.BlockCodec(k, bs)
+    raw = _t(data)
+    slots, sizes = codec.compress(raw)
+    nb = codec.n_blocks(n)
+    torch.cuda.synchronize()
+    sz = sizes.cpu().numpy()
+    sl = slots.cpu().numpy()
+    for b in range(nb):
+        blk = sl[b * codec.slot_stride: b * codec.slot_stride + sz[b]].tobytes()
+        assert blk == oracle.compress(k, data[b * bs: (b + 1) * bs]), (k, bs, b)
+    # decode straight from the slots
+    out = codec.decompress(slots, codec.slot_offsets(n), sizes, n)
+    assert out[:n].cpu().numpy().tobytes() == data
+    # and from the packed layout
+    packed, offsets, total = codec.pack(slots, sizes, nb)
+    assert int(total.item()) == int(sz[:nb].sum())
+    assert np.array_equal(offsets[:nb].cpu().numpy(), np.concatenate([[0], np.cumsum(sz[:nb])[:-1]]))
+    out2 = codec.decompress(packed, offsets, sizes, n)
+    assert out2[:n].cpu().numpy().tobytes() == data
+
+
+def test_histogram_dev_large(huf):
+    import torch
+    n = (1 << 28) + 12345
+    g = torch.Generator(device="cuda").manual_seed(1)
+    raw = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    raw[: n // 2] = 65  # skewed half
+    codec = huf.BlockCodec(32, 131072)
+    h = codec.histogram(raw)
+    want = torch.bincount(raw.to(torch.int32), minlength=256)  # checker only
+    assert torch.equal(h, want.to(torch.int64))
+    assert int(h.sum().item()) == n
+
+
+def test_shared_table_mode(huf, oracle):
+    import torch
+    k, bs = 32, 131072
+    data = english(4 * bs, seed=3)
+    codec = huf.BlockCodec(k, bs)
+    raw = _t(data)
+    hist = codec.histogram(raw)
+    table = codec.build_table(hist)
+    slots, sizes = codec.compress(raw, table=table)
+    torch.cuda.synchronize()
+    cd = oracle.make_coding(oracle.histogram(data))
+    sz = sizes.cpu().numpy()
+    sl = slots.cpu().numpy()
+    for b in range(4):
+        blk = sl[b * codec.slot_stride: b * codec.slot_stride + sz[b]].tobytes()
+        want = oracle.compress_with_table(k, data[b * bs: (b + 1) * bs], cd["len_count"], cd["sorted_syms"])
+        assert blk == want, b
+    out = codec.decompress(slots, codec.slot_offsets(len(data)), sizes, len(data))
+    assert out.cpu().numpy().tobytes() == data
+
+
+def test_full_size_roundtrip_properties(huf, oracle):
+    """BASELINE config 2 at full size (1 GiB, 128 KiB x 32): size-independent properties --
+    decode(encode(x)) == x on the device, sum of block sizes == packed size, and a seeded
+    sample of blocks byte-equal to the oracle."""
+    import torch
+    k, bs, n = 32, 131072, 1 << 30
+    g = torch.Generator(device="cuda").manual_seed(2)
+    u = torch.rand(n, device="cuda", generator=g).clamp_(min=1e-30)
+    raw = (torch.floor(torch.log(u) / np.log(0.8)).to(torch.int64) % 256).to(torch.uint8)
+    del u
+    codec = huf.BlockCodec(k, bs)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    slots, sizes = codec.compress(raw, status=status)
+    out = codec.decompress(slots, codec.slot_offsets(n), sizes, n, status=status)
+    assert int(status.item()) == 0
+    assert torch.equal(out, raw)
+    nb = codec.n_blocks(n)
+    sz = sizes.cpu().numpy().astype(np.int64)
+    ratio = sz.sum() / n
+    assert 0.44 < ratio < 0.48, ratio
+    rng = np.random.default_rng(0)
+    for b in [0, nb - 1] + list(rng.integers(0, nb, 14)):
+        b = int(b)
+        blk = slots[b * codec.slot_stride: b * codec.slot_stride + int(sz[b])].cpu().numpy().tobytes()
+        assert blk == oracle.compress(k, raw[b * bs: (b + 1) * bs].cpu().numpy().tobytes()), b

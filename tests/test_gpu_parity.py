@@ -1,0 +1,168 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the
+same inputs -- bit-exact, both directions.  Re-hosts the reference's CompressorTest /
+HistogramTest suites (codec/huffman_test.cpp:47-184, codec/histogram_test.cpp:13-52) with
+round-trip checks upgraded to byte equality of the compressed image and cross-decoding."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from _cases import GOLDEN, KS, extra_cases, golden, reference_test_cases, biased, english
+
+pytestmark = pytest.mark.gpu
+
+ALL_CASES = reference_test_cases() + extra_cases()
+
+
+@pytest.mark.parametrize("k", KS)
+def test_compress_matches_oracle_and_cross_decodes(huf, oracle, k):
+    for name, data in ALL_CASES:
+        want = oracle.compress(k, data)
+        got = huf.compress(k, data)
+        assert got == want, f"{name} K={k}: compressed image differs ({len(got)} vs {len(want)} bytes)"
+        assert huf.decompress(k, want) == data, f"{name} K={k}: GPU decode of oracle stream"
+        assert oracle.decompress(k, got) == data, f"{name} K={k}: oracle decode of GPU stream"
+
+
+def test_compress_matches_golden_vectors(huf):
+    vec = json.load(open(os.path.join(GOLDEN, "vectors.json")))["compress"]
+    cases = dict(ALL_CASES)
+    n = 0
+    for key, ent in vec.items():
+        name, ks = key.split("/K")
+        got = huf.compress(int(ks), cases[name])
+        assert len(got) == ent["comp_len"], key
+        assert hashlib.sha256(got).hexdigest() == ent["sha256"], key
+        if "hex" in ent:
+            assert got.hex() == ent["hex"], key
+        n += 1
+    assert n > 150
+
+
+def test_compress_matches_reference_build(huf, ref):
+    """Against the unmodified reference where it was built (skipped if oracle/_ref is absent)."""
+    for name, data in ALL_CASES[:12] + extra_cases():
+        for k in (4, 32, 48):
+            assert huf.compress(k, data) == ref.compress(k, data), (name, k)
+            for variant in (ref.GATHER, ref.PERMUTE) if k % 8 == 0 else ():
+                assert huf.decompress(k, ref.compress(k, data, variant)) == data
+                assert ref.decompress(k, huf.compress(k, data), variant) == data
+
+
+def test_odd_stream_counts(huf, oracle):
+    for k in (3, 5, 7, 24, 40, 64):
+        for name, data in extra_cases():
+            got = huf.compress(k, data)
+            assert got == oracle.compress(k, data), (name, k)
+            assert huf.decompress(k, got) == data, (name, k)
+
+
+def test_histogram(huf, oracle):
+    # HistogramTest.ShortSanity / Long (codec/histogram_test.cpp:18-42)
+    h = huf.MakeHistogram(b"foobar")
+    assert (h[ord("f")], h[ord("o")], h[ord("b")], h[ord("a")], h[ord("r")], h[ord("q")]) == (1, 2, 1, 1, 1, 0)
+    for data in (golden("long_random.bin")[:2007], golden("hist_biased_3125.bin"), golden("uniform_100k.bin"),
+                 b"", b"z", biased(1 << 20, seed=9), bytes(1 << 16), english(333_333, seed=2)):
+        assert np.array_equal(huf.MakeHistogram(data), oracle.histogram(data))
+    # unaligned views
+    buf = np.frombuffer(biased(300_001, seed=4), dtype=np.uint8)
+    for off in (1, 3, 7, 15):
+        assert np.array_equal(huf.MakeHistogram(buf[off:]), oracle.histogram(buf[off:].tobytes()))
+
+
+def test_table_build_matches_oracle(huf, oracle):
+    rng = np.random.default_rng(7)
+    hists = [oracle.histogram(d) for _, d in ALL_CASES[:10] + extra_cases()]
+    # tie-heavy histograms: the order of equal counts must follow libstdc++'s introsort
+    for n in (1, 2, 3, 15, 16, 17, 33, 64, 100, 200, 256):
+        for hi in (1, 2, 3, 10):
+            h = np.zeros(256, dtype=np.uint32)
+            idx = rng.permutation(256)[:n]
+            h[idx] = rng.integers(1, hi + 1, n)
+            hists.append(h)
+    # median-of-three killer style patterns and long-code histograms
+    h = np.zeros(256, dtype=np.uint32)
+    h[:] = np.arange(256, 0, -1)
+    hists.append(h)
+    h = np.zeros(256, dtype=np.uint32)
+    h[:40] = [min(2 ** i, 2 ** 31) for i in range(40)]
+    hists.append(h)
+    for h in hists:
+        want = oracle.make_coding(h)
+        got = huf.make_table(h)
+        assert got["num_syms"] == want["num_syms"]
+        assert got["len_mask"] == want["len_mask"]
+        assert np.array_equal(got["len_count"], want["len_count"])
+        assert got["sorted_syms"] == want["sorted_syms"]
+        assert np.array_equal(got["code_len"], want["code_len"])
+        assert np.array_equal(got["code_bits"], want["code_bits"])
+
+
+def test_decode_table_matches_oracle(huf, oracle):
+    for _, data in ALL_CASES[:10] + extra_cases():
+        if not data:
+            continue
+        cd = oracle.make_coding(oracle.histogram(data))
+        want = oracle.dtable(2, cd["len_count"], cd["sorted_syms"])
+        got = huf.decode_table(cd["len_count"], cd["sorted_syms"])
+        assert np.array_equal(got, want)
+
+
+def test_compress_with_table(huf, oracle):
+    data = golden("proba02_100k.bin")
+    other = biased(50_000, seed=11)
+    cd = oracle.make_coding(oracle.histogram(data))  # table from a different buffer
+    for k in (4, 32):
+        want = oracle.compress_with_table(k, other, cd["len_count"], cd["sorted_syms"])
+        got = huf.compress_with_table(k, other, cd["len_count"], cd["sorted_syms"])
+        assert got == want
+        assert huf.decompress(k, got) == other
+    # a symbol without a code must be reported, not encoded
+    with pytest.raises(huf.HufError) as ei:
+        huf.compress_with_table(4, b"\xff" * 100, cd["len_count"], cd["sorted_syms"])
+    assert ei.value.code == -4
+
+
+def test_error_paths(huf):
+    with pytest.raises(huf.HufError) as ei:
+        huf.compress(0, b"abc")
+    assert ei.value.code == -1
+    with pytest.raises(huf.HufError) as ei:
+        huf.compress(65, b"abc")
+    assert ei.value.code == -1
+    good = huf.compress(4, b"hello hello hello")
+    with pytest.raises(huf.HufError):
+        huf.decompress(4, good[:6])
+    bad = bytearray(good)
+    bad[4] = 0xff
+    bad[5] = 0xff  # length mask with bits above 12
+    with pytest.raises(huf.HufError) as ei:
+        huf.decompress(4, bytes(bad))
+    assert ei.value.code == -4
+    # truncated payload must not crash the device
+    try:
+        huf.decompress(4, good[:-9])
+    except huf.HufError:
+        pass
+    assert huf.decompress(4, good) == b"hello hello hello"
+
+
+def test_block_container_roundtrip(huf, oracle):
+    data = biased(1_000_000, seed=21)
+    for k, bs in ((32, 131072), (4, 16384), (48, 65536), (8, 1 << 20)):
+        cont = huf.compress_blocks(k, bs, data)
+        assert huf.decompress_blocks(cont) == data
+        # every block is an independent reference-format buffer
+        nb = (len(data) + bs - 1) // bs
+        sizes = np.frombuffer(cont[32: 32 + 4 * nb], dtype="<u4")
+        pos = 32 + 4 * nb
+        for b in range(nb):
+            blk = cont[pos: pos + int(sizes[b])]
+            pos += int(sizes[b])
+            raw_blk = data[b * bs: (b + 1) * bs]
+            if b in (0, nb - 1) or b % 3 == 0:
+                assert blk == oracle.compress(k, raw_blk), (k, bs, b)
+        assert pos == len(cont)
+    assert huf.decompress_blocks(huf.compress_blocks(32, 131072, b"")) == b""
