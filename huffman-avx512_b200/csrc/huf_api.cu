@@ -108,8 +108,7 @@ int decode_bpc(int k) {
 }
 
 int compress_grid(uint32_t n_blocks, int sms) {
-  // 41.8 KB static smem + 512 threads: up to 4 CTAs per SM
-  const uint32_t cap = (uint32_t)sms * 4u;
+  const uint32_t cap = (uint32_t)sms * (uint32_t)kCompCtasPerSm;
   return (int)(n_blocks < cap ? n_blocks : cap);
 }
 

@@ -29,11 +29,12 @@ struct HufTable {
 
 // Scratch for the table build (shared memory, one per CTA).
 struct TableScratch {
-  unsigned long long keys[256];        // (count << 8) | symbol, sorted by count descending
-  unsigned long long tree_count[256];  // internal-node weights (tree_count, :365)
-  uint16_t node_parent[256];
+  unsigned long long keys[256];        // (count << 8) | symbol; u32 view when every count < 2^24
+  unsigned long long tree_count[256];  // sorted keys (u64 mode) / internal-node weights (:365)
   uint16_t leaf_parent[256];
-  uint16_t node_depth[256];
+  uint16_t par[2][256];                // pointer-jumping ping-pong: ancestor link
+  uint16_t dep[2][256];                // pointer-jumping ping-pong: distance to that ancestor
+  int32_t st_first[20], st_last[20], st_depth[20];  // explicit introsort stack
   uint32_t len_count33[36];            // depth histogram before limiting (:290, :329-337)
   uint32_t cum[16];                    // inclusive prefix of len_count
   uint32_t start_code[16];             // first left-aligned code of each length
@@ -59,24 +60,28 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 }
 
 // ---------------------------------------------------------------------------
-// libstdc++ std::sort clone (GCC 13 bits/stl_algo.h, bits/stl_heap.h) run by ONE
-// thread on the key array.  The reference sorts the present symbols with a
-// comparator that ignores the symbol value (codec/huffman.cpp:353-354), so the
-// order of equal-count symbols -- and with it sorted_syms, every code and every
-// compressed byte -- is whatever introsort leaves.  Reproducing
-// it exactly is the only way to emit the reference's bytes.
+// Exact emulation of libstdc++'s std::sort (GCC 13 bits/stl_algo.h, bits/stl_heap.h).
+// The reference sorts the present symbols with a comparator that ignores the symbol
+// value (codec/huffman.cpp:353-354), so the order of equal-count symbols -- and with it
+// sorted_syms, every code and every compressed byte -- is whatever introsort leaves
+// (SURVEY.md H1).  std::sort = __introsort_loop (partitions down to ranges of <= 16,
+// heapsort when the depth limit 2*floor(log2 n) is exhausted) followed by
+// __final_insertion_sort.  The insertion sort never moves an element past an equal one,
+// i.e. it is a STABLE sort of whatever the partition phase left.  So only the partition
+// phase (inherently serial, ~n log(n/16) steps, skipped for n <= 16) is run by one
+// thread; the final pass is replaced by a parallel stable rank computation.
 // less(a, b) <=> count(a) > count(b), count = key >> 8.
 // ---------------------------------------------------------------------------
 namespace sortclone {
-typedef unsigned long long key_t;
-__device__ __forceinline__ bool less(key_t a, key_t b) { return (a >> 8) > (b >> 8); }
-__device__ __forceinline__ void swp(key_t* a, int i, int j) {
-  key_t t = a[i];
+template <typename K> __device__ __forceinline__ bool less(K a, K b) { return (a >> 8) > (b >> 8); }
+template <typename K> __device__ __forceinline__ void swp(K* a, int i, int j) {
+  K t = a[i];
   a[i] = a[j];
   a[j] = t;
 }
 
-__device__ inline void push_heap(key_t* a, int first, int hole, int top, key_t value) {
+template <typename K>
+__device__ inline void push_heap(K* a, int first, int hole, int top, K value) {
   int parent = (hole - 1) / 2;
   while (hole > top && less(a[first + parent], value)) {
     a[first + hole] = a[first + parent];
@@ -86,7 +91,8 @@ __device__ inline void push_heap(key_t* a, int first, int hole, int top, key_t v
   a[first + hole] = value;
 }
 
-__device__ inline void adjust_heap(key_t* a, int first, int hole, int len, key_t value) {
+template <typename K>
+__device__ inline void adjust_heap(K* a, int first, int hole, int len, K value) {
   const int top = hole;
   int child = hole;
   while (child < (len - 1) / 2) {
@@ -104,12 +110,13 @@ __device__ inline void adjust_heap(key_t* a, int first, int hole, int len, key_t
 }
 
 // std::__partial_sort(first, last, last): make_heap + sort_heap
-__device__ inline void heap_sort(key_t* a, int first, int last) {
+template <typename K>
+__device__ inline void heap_sort(K* a, int first, int last) {
   int len = last - first;
   if (len >= 2) {
     int parent = (len - 2) / 2;
     for (;;) {
-      key_t v = a[first + parent];
+      K v = a[first + parent];
       adjust_heap(a, first, parent, len, v);
       if (parent == 0) break;
       parent--;
@@ -117,118 +124,93 @@ __device__ inline void heap_sort(key_t* a, int first, int last) {
   }
   while (last - first > 1) {
     --last;
-    key_t v = a[last];
+    K v = a[last];
     a[last] = a[first];
     adjust_heap(a, first, 0, last - first, v);
   }
 }
 
-__device__ inline void linear_insert(key_t* a, int last) {
-  key_t val = a[last];
-  int next = last - 1;
-  while (less(val, a[next])) {
-    a[last] = a[next];
-    last = next;
-    --next;
-  }
-  a[last] = val;
-}
-
-__device__ inline void insertion_sort(key_t* a, int first, int last) {
-  if (first == last) return;
-  for (int i = first + 1; i != last; ++i) {
-    if (less(a[i], a[first])) {
-      key_t val = a[i];
-      for (int j = i; j > first; --j) a[j] = a[j - 1];
-      a[first] = val;
-    } else {
-      linear_insert(a, i);
-    }
-  }
-}
-
-__device__ inline void sort(key_t* a, int n) {
-  if (n <= 1) return;
-  if (n > 16) {
-    int lg = 31 - __clz(n);
-    // explicit stack instead of the recursion on the right part; the two parts are
-    // disjoint, so the order in which they are processed does not change the result
-    int st_first[40], st_last[40], st_depth[40];
-    int sp = 0;
-    int first = 0, last = n, depth = 2 * lg;
-    for (;;) {
-      while (last - first > 16) {
-        if (depth == 0) {
-          heap_sort(a, first, last);
-          break;
-        }
-        --depth;
-        // __unguarded_partition_pivot
-        const int mid = first + (last - first) / 2;
-        {  // __move_median_to_first(first, first+1, mid, last-1)
-          const int ia = first + 1, ib = mid, ic = last - 1;
-          if (less(a[ia], a[ib])) {
-            if (less(a[ib], a[ic])) swp(a, first, ib);
-            else if (less(a[ia], a[ic])) swp(a, first, ic);
-            else swp(a, first, ia);
-          } else if (less(a[ia], a[ic])) swp(a, first, ia);
-          else if (less(a[ib], a[ic])) swp(a, first, ic);
-          else swp(a, first, ib);
-        }
-        int lo = first + 1, hi = last;
-        const key_t pivot_unused = 0;
-        (void)pivot_unused;
-        for (;;) {  // __unguarded_partition(first+1, last, first); the pivot stays at a[first]
-          while (less(a[lo], a[first])) ++lo;
-          --hi;
-          while (less(a[first], a[hi])) --hi;
-          if (!(lo < hi)) break;
-          swp(a, lo, hi);
-          ++lo;
-        }
-        const int cut = lo;
-        // right part [cut, last) is pushed, left part [first, cut) continues
-        st_first[sp] = cut;
-        st_last[sp] = last;
-        st_depth[sp] = depth;
-        ++sp;
-        last = cut;
+// std::__introsort_loop on a[0..n), n > 16: ONE thread.  The recursion on the right part is an
+// explicit stack; the two parts are disjoint so their processing order does not matter.
+template <typename K>
+__device__ inline void partition_phase(K* a, int n, int32_t* st_first, int32_t* st_last, int32_t* st_depth) {
+  int sp = 0;
+  int first = 0, last = n, depth = 2 * (31 - __clz(n));
+  for (;;) {
+    while (last - first > 16) {
+      if (depth == 0) {
+        heap_sort(a, first, last);
+        break;
       }
-      if (sp == 0) break;
-      --sp;
-      first = st_first[sp];
-      last = st_last[sp];
-      depth = st_depth[sp];
+      --depth;
+      const int mid = first + (last - first) / 2;
+      {  // __move_median_to_first(first, first+1, mid, last-1)
+        const K ka = a[first + 1], kb = a[mid], kc = a[last - 1];
+        int pick;
+        if (less(ka, kb)) {
+          if (less(kb, kc)) pick = mid;
+          else if (less(ka, kc)) pick = last - 1;
+          else pick = first + 1;
+        } else if (less(ka, kc)) pick = first + 1;
+        else if (less(kb, kc)) pick = last - 1;
+        else pick = mid;
+        swp(a, first, pick);
+      }
+      // __unguarded_partition(first+1, last, pivot = *first)
+      const K pivot = a[first];
+      int lo = first + 1, hi = last;
+      for (;;) {
+        K kl = a[lo];
+        while (less(kl, pivot)) kl = a[++lo];
+        K kh = a[--hi];
+        while (less(pivot, kh)) kh = a[--hi];
+        if (!(lo < hi)) break;
+        a[lo] = kh;
+        a[hi] = kl;
+        ++lo;
+      }
+      st_first[sp] = lo;  // right part [cut, last) for later, left part [first, cut) now
+      st_last[sp] = last;
+      st_depth[sp] = depth;
+      ++sp;
+      last = lo;
     }
-    // __final_insertion_sort
-    insertion_sort(a, 0, 16);
-    for (int i = 16; i != n; ++i) linear_insert(a, i);
-  } else {
-    insertion_sort(a, 0, n);
+    if (sp == 0) break;
+    --sp;
+    first = st_first[sp];
+    last = st_last[sp];
+    depth = st_depth[sp];
   }
 }
 }  // namespace sortclone
 
 // ---------------------------------------------------------------------------
 // Table build, executed by ONE WARP (all 32 lanes must call it).
-//   hist  : 256 counts (shared or global memory), CountT = uint32_t or uint64_t
+//   hist  : 256 counts (shared memory), CountT = uint32_t or uint64_t
+//   KeyT  : uint32_t when every count < 2^24, else unsigned long long
 //   tab   : output (shared memory)
 // Restates MakeCanonicalCoding (codec/huffman.cpp:339-437): present symbols ->
 // std::sort by count descending -> two-queue Huffman merge (leaf preferred on
 // ties, :375) -> depth histogram -> LimitCodeLengths (:297-327) -> canonical
 // codes (ForallCodes, :260-284).
 // ---------------------------------------------------------------------------
-template <typename CountT>
+template <typename CountT, typename KeyT>
 __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, TableScratch* sc) {
   const int lane = lane_id();
+  // u32 keys: keys[] in the first, the sorted copy in the second half of sc->keys, node
+  // weights in sc->tree_count.  u64 keys: keys[] = sc->keys, sorted copy = sc->tree_count,
+  // node weights overwrite sc->keys (free once the sorted copy exists).
+  KeyT* keys = reinterpret_cast<KeyT*>(sc->keys);
+  KeyT* sorted = sizeof(KeyT) == 8 ? reinterpret_cast<KeyT*>(sc->tree_count) : keys + 256;
+  CountT* tree = sizeof(KeyT) == 8 ? reinterpret_cast<CountT*>(sc->keys) : reinterpret_cast<CountT*>(sc->tree_count);
   // 1. present symbols in ascending symbol order (:342-347)
   int n = 0;
 #pragma unroll 1
   for (int base = 0; base < 256; base += 32) {
     const int c = base + lane;
-    const unsigned long long cnt = (unsigned long long)hist[c];
+    const CountT cnt = hist[c];
     const unsigned m = __ballot_sync(0xffffffffu, cnt != 0);
-    if (cnt != 0) sc->keys[n + __popc(m & ((1u << lane) - 1))] = (cnt << 8) | (unsigned)c;
+    if (cnt != 0) keys[n + __popc(m & ((1u << lane) - 1))] = ((KeyT)cnt << 8) | (KeyT)c;
     n += __popc(m);
   }
   for (int i = lane; i < 256; i += 32) tab->enc[i] = kEncInvalid;
@@ -236,47 +218,80 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
   __syncwarp();
 
   if (n > 0) {
-    // 2. sort + 3. Huffman merge: inherently serial, lane 0 only
-    if (lane == 0) {
-      sortclone::sort(sc->keys, n);
-      int next_sym = n - 1, next_node = 0, tree_size = 0;
-      while ((tree_size - next_node) + (next_sym + 1) > 1) {
-        unsigned long long sum = 0;
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          bool take_leaf = false;
-          if (next_sym >= 0) {
-            if (next_node == tree_size) take_leaf = true;
-            else take_leaf = (sc->keys[next_sym] >> 8) <= sc->tree_count[next_node];  // :375
-          }
-          if (take_leaf) {
-            sum += sc->keys[next_sym] >> 8;
-            sc->leaf_parent[next_sym] = (uint16_t)tree_size;
-            --next_sym;
-          } else {
-            sum += sc->tree_count[next_node];
-            sc->node_parent[next_node] = (uint16_t)tree_size;
-            ++next_node;
-          }
-        }
-        sc->tree_count[tree_size] = sum;
-        ++tree_size;
+    // 2a. introsort partition phase (serial, only for n > 16)
+    if (n > 16) {
+      if (lane == 0) sortclone::partition_phase(keys, n, sc->st_first, sc->st_last, sc->st_depth);
+      __syncwarp();
+    }
+    // 2b. final insertion sort == stable sort: rank = #greater + #equal-before
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const KeyT mine = i < n ? keys[i] : 0;
+      const KeyT mc = mine >> 8;
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const KeyT oc = keys[j] >> 8;  // broadcast read
+        rank += ((oc > mc) || (oc == mc && j < i)) ? 1 : 0;
       }
-      if (tree_size == 0) {
-        sc->len_count33[0] = 1;  // one symbol: the root is a leaf at depth 0 (:417-418)
-      } else {
-        sc->node_depth[tree_size - 1] = 0;
-        for (int node = tree_size - 2; node >= 0; --node)
-          sc->node_depth[node] = sc->node_depth[sc->node_parent[node]] + 1;
-      }
+      if (i < n) sorted[rank] = mine;
     }
     __syncwarp();
-    // 4. depth histogram over the leaves (CollectCodeLen, :329-337)
+    // 3. two-queue Huffman merge: inherently serial; the queue heads live in registers
+    const int n_nodes = n - 1;
+    if (lane == 0 && n > 1) {
+      int ls = n - 1, nh = 0;
+      CountT L0 = (CountT)(sorted[ls] >> 8);
+      CountT L1 = (CountT)(sorted[ls - 1] >> 8);
+      CountT N0 = 0, N1 = 0;
+      for (int m = 0; m < n_nodes; ++m) {
+        CountT sum = 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const bool leaf = (ls >= 0) && (nh == m || L0 <= N0);  // :370-376
+          if (leaf) {
+            sum += L0;
+            sc->leaf_parent[ls] = (uint16_t)m;
+            --ls;
+            L0 = L1;
+            L1 = ls >= 1 ? (CountT)(sorted[ls - 1] >> 8) : (CountT)0;
+          } else {
+            sum += N0;
+            sc->par[0][nh] = (uint16_t)m;
+            ++nh;
+            N0 = N1;
+            N1 = nh + 1 < m ? tree[nh + 1] : (CountT)0;
+          }
+        }
+        tree[m] = sum;  // u32 wrap-around like the reference when CountT is u32 (:365, :414)
+        if (nh == m) N0 = sum;
+        else if (nh + 1 == m) N1 = sum;
+      }
+      sc->par[0][n_nodes - 1] = (uint16_t)(n_nodes - 1);  // the root points at itself
+    }
+    __syncwarp();
+    // 4. node depths by pointer jumping (8 synchronous rounds cover any depth <= 255), then
+    //    the leaf depth histogram (CollectCodeLen, :329-337)
     if (n > 1) {
+      for (int i = lane; i < n_nodes; i += 32) sc->dep[0][i] = (i == n_nodes - 1) ? 0 : 1;
+      __syncwarp();
+      int cur = 0;
+#pragma unroll 1
+      for (int round = 0; round < 8; ++round) {
+        for (int i = lane; i < n_nodes; i += 32) {
+          const int p = sc->par[cur][i];
+          sc->dep[cur ^ 1][i] = sc->dep[cur][i] + sc->dep[cur][p];
+          sc->par[cur ^ 1][i] = sc->par[cur][p];
+        }
+        cur ^= 1;
+        __syncwarp();
+      }
       for (int i = lane; i < n; i += 32) {
-        int d = sc->node_depth[sc->leaf_parent[i]] + 1;
+        const int d = sc->dep[cur][sc->leaf_parent[i]] + 1;
         atomicAdd(&sc->len_count33[d > 32 ? 32 : d], 1u);
       }
+    } else if (lane == 0) {
+      sc->len_count33[0] = 1;  // one symbol: the root is a leaf at depth 0 (:417-418)
     }
     __syncwarp();
     // 5. LimitCodeLengths (:297-327), serial and tiny
@@ -316,7 +331,7 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
     __syncwarp();
     // 6. canonical codes (ForallCodes, :260-284), one symbol per lane
     for (int i = lane; i < n; i += 32) {
-      const unsigned sym = (unsigned)(sc->keys[i] & 0xffu);
+      const unsigned sym = (unsigned)(sorted[i] & 0xffu);
       tab->sorted_syms[i] = (uint8_t)sym;
       int l = 0;
       while (l < kMaxCodeLen && (uint32_t)i >= sc->cum[l]) ++l;

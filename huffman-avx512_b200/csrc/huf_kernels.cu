@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(32) k_build_table(const unsigned long long* __
   __shared__ unsigned long long h[256];
   for (int i = threadIdx.x; i < 256; i += 32) h[i] = hist[i];
   __syncwarp();
-  build_table_warp<unsigned long long>(h, &tab, &sc);
+  build_table_warp<unsigned long long, unsigned long long>(h, &tab, &sc);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(&tab);
   uint32_t* dst = reinterpret_cast<uint32_t*>(out);
   for (int i = threadIdx.x; i < (int)(sizeof(HufTable) / 4); i += 32) dst[i] = src[i];
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(32) k_make_table(const uint32_t* __restrict__ 
   if (mode == 0) {
     for (int i = threadIdx.x; i < 256; i += 32) h[i] = hist[i];
     __syncwarp();
-    build_table_warp<uint32_t>(h, &tab, &sc);
+    build_table_warp<uint32_t, unsigned long long>(h, &tab, &sc);
   } else {
     for (int i = threadIdx.x; i < 13; i += 32) lc[i] = in_len_count[i];
     for (int i = threadIdx.x; i < in_n; i += 32) sy[i] = in_syms[i];
@@ -299,7 +299,7 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t* ring, c
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kCompThreads)
+__global__ void __launch_bounds__(kCompThreads, kCompCtasPerSm)
 k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_size, int K,
                   uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
                   uint32_t* __restrict__ comp_sizes, const HufTable* __restrict__ shared_tab,
@@ -333,7 +333,8 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       uint32_t* d = reinterpret_cast<uint32_t*>(&sm.tab);
       for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += kCompThreads) d[i] = s[i];
     } else if (warp == 0) {
-      build_table_warp<uint32_t>(sm.hist, &sm.tab, &sm.sc);
+      if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist, &sm.tab, &sm.sc);
+      else build_table_warp<uint32_t, unsigned long long>(sm.hist, &sm.tab, &sm.sc);
     }
     {
       uint32_t* rz = &sm.u.ring[0][0];
@@ -430,36 +431,59 @@ struct DecBlockInfo {
   uint32_t first_idx[16];  // index into sorted_syms of the first code of each length
 };
 
-// Table entry: byte0 = bits consumed, byte1 = sym0, byte2 = sym1, byte3 = num_syms | len(sym0)<<4
-// (DecodedSym2x, :634-640, plus the first code's own length in the spare nibble).
+// Decode table over the next BITS bits of the stream (Decoder2x, codec/huffman.cpp:642-704).
+// Entry: byte0 = sym0, byte1 = sym1, byte2 = bits consumed, byte3 = number of symbols (1 or 2).
+//   BITS = 12: exactly the reference's two-symbol table (pair taken iff l1 + l2 <= 12, :653).
+//   BITS = 11: what the decode kernel uses (8 KiB instead of 16 KiB per block doubles the
+//   resident warps).  A 12-bit code cannot be resolved by 11 bits, but 12-bit codes come in
+//   sibling pairs that share their first 11 bits (the code is complete), so such an entry
+//   carries both candidates (sym0 for next bit 0, sym1 for next bit 1), bits = 12, 1 symbol;
+//   pairs are taken iff l1 + l2 <= 11.
+// During construction bits 26..29 of an entry hold the first code's own length.
+template <int BITS>
 __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, int tid,
                                     int nthreads) {
-  for (int e = tid; e < 4096; e += nthreads) {
+  constexpr int N = 1 << BITS;
+  constexpr int SH = kMaxCodeLen - BITS;
+  for (int e = tid; e < N; e += nthreads) {
+    const uint32_t v = (uint32_t)e << SH;  // left-aligned 12-bit value of this prefix
     int l = 0;
-    while (l <= kMaxCodeLen && (uint32_t)e >= bi->code_end[l]) ++l;
+    while (l <= BITS && v >= bi->code_end[l]) ++l;
     uint32_t ent;
-    if (l > kMaxCodeLen) {
-      ent = 12u | (1u << 24) | (12u << 28);  // not covered by any code (malformed table)
-    } else {
+    if (l <= BITS) {
       const uint32_t lo = l ? bi->code_end[l - 1] : 0u;
-      const uint32_t idx = bi->first_idx[l] + (((uint32_t)e - lo) >> (kMaxCodeLen - l));
+      const uint32_t idx = bi->first_idx[l] + ((v - lo) >> (kMaxCodeLen - l));
       const uint32_t sym = idx < bi->num_syms ? syms[idx] : 0u;
-      ent = (uint32_t)l | (sym << 8) | (1u << 24) | ((uint32_t)l << 28);
+      ent = sym | ((uint32_t)l << 16) | (1u << 24) | ((uint32_t)l << 26);
+    } else if (BITS < kMaxCodeLen && v < bi->code_end[kMaxCodeLen]) {
+      const uint32_t idx = bi->first_idx[kMaxCodeLen] + (v - bi->code_end[kMaxCodeLen - 1]);
+      const uint32_t s0 = idx < bi->num_syms ? syms[idx] : 0u;
+      const uint32_t s1 = idx + 1 < bi->num_syms ? syms[idx + 1] : 0u;
+      ent = s0 | (s1 << 8) | (12u << 16) | (1u << 24) | (12u << 26);
+    } else {
+      ent = (12u << 16) | (1u << 24) | (12u << 26);  // not covered by any code (malformed table)
     }
     T[e] = ent;
   }
   __syncthreads();
-  for (int e = tid; e < 4096; e += nthreads) {
+  for (int e = tid; e < N; e += nthreads) {
     const uint32_t e1 = T[e];
-    const uint32_t l1 = e1 >> 28;
-    const uint32_t rest = ((uint32_t)e << l1) & 0xfffu;
-    const uint32_t e2 = T[rest];
-    const uint32_t l2 = e2 >> 28;
-    if (l1 + l2 <= (uint32_t)kMaxCodeLen)  // :653
-      T[e] = (l1 + l2) | (e1 & 0xff00u) | ((e2 & 0xff00u) << 8) | (2u << 24) | (l1 << 28);
+    const uint32_t l1 = (e1 >> 26) & 15u;
+    if (l1 <= (uint32_t)BITS) {
+      const uint32_t rest = ((uint32_t)e << l1) & (uint32_t)(N - 1);
+      const uint32_t e2 = T[rest];  // sym0 / own-length fields are never rewritten
+      const uint32_t l2 = (e2 >> 26) & 15u;
+      if (l1 + l2 <= (uint32_t)BITS)  // :653
+        T[e] = (e1 & 0xffu) | ((e2 & 0xffu) << 8) | ((l1 + l2) << 16) | (2u << 24) | (l1 << 26);
+    }
   }
   __syncthreads();
+  for (int e = tid; e < N; e += nthreads) T[e] &= 0x03ffffffu;
+  __syncthreads();
 }
+
+constexpr int kDecBits = 11;
+constexpr int kDecEntries = 1 << kDecBits;
 
 __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
                                     DecBlockInfo* bi) {
@@ -509,11 +533,11 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
                     uint8_t* __restrict__ raw, uint64_t raw_n, uint32_t block_size,
                     uint32_t* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  // layout: tables [bpc][4096] u32 | rings [nwarps][16][32] u32 | rows [nthreads][20] u8 | infos [bpc]
+  // layout: tables [bpc][2048] u32 | rings [nwarps][16][32] u32 | rows [nthreads][20] u8 | infos [bpc]
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
   uint32_t* tables = reinterpret_cast<uint32_t*>(dsm);
-  uint32_t* rings = tables + (size_t)bpc * 4096;
+  uint32_t* rings = tables + (size_t)bpc * kDecEntries;
   uint8_t* rows = reinterpret_cast<uint8_t*>(rings + (size_t)nwarps * 16 * 32);
   DecBlockInfo* infos = reinterpret_cast<DecBlockInfo*>(rows + (((size_t)nthreads * 20 + 15) & ~(size_t)15));
 
@@ -539,7 +563,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   for (int lb = 0; lb < bpc; ++lb) {
     const DecBlockInfo* bi = &infos[lb];
     if (b0 + lb < n_blocks && bi->ok && bi->raw_size != 0) {
-      build_dtable(bi, comp + offsets[b0 + lb] + bi->syms_off, tables + (size_t)lb * 4096, tid, nthreads);
+      build_dtable<kDecBits>(bi, comp + offsets[b0 + lb] + bi->syms_off, tables + (size_t)lb * kDecEntries, tid, nthreads);
     }
   }
   __syncthreads();
@@ -584,12 +608,12 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   }
   if (bad_lane && status) atomicOr(status, 1u);
 
-  const uint32_t* T = tables + (size_t)(lb < bpc ? lb : 0) * 4096;
+  const uint32_t* T = tables + (size_t)(lb < bpc ? lb : 0) * kDecEntries;
   uint32_t* col = rings + (size_t)warp * 16 * 32 + lane;  // word i at col[(i & 15) * 32]
   uint8_t* row = rows + (size_t)tid * 20;
 
-  // prime: stage 3 chunks (12 words), keep two more in registers
-  uint4 p0, p1;
+  // prime: stage 3 chunks (12 words) and keep the next one in registers
+  uint4 pf;
   {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -601,9 +625,8 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       staged += 4;
       ++cidx;
     }
-    p0 = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
-    p1 = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 2), lo_lim) : make_uint4(0, 0, 0, 0);
-    cidx += 2;
+    pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
+    ++cidx;
   }
   uint32_t hi = col[(rd & 15) * 32];
   uint32_t lo = col[((rd + 1) & 15) * 32];
@@ -613,28 +636,27 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t cnt = 0;  // symbols already sitting in row[] (0 or 1 carried over)
   const uint32_t max_left = __reduce_max_sync(0xffffffffu, left);
   for (uint32_t round = 0; round * 16 < max_left; ++round) {
-    // top up the ring: a round consumes at most 7 words
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (staged - rd < 8) {
-        col[((staged + 0) & 15) * 32] = p0.w;
-        col[((staged + 1) & 15) * 32] = p0.z;
-        col[((staged + 2) & 15) * 32] = p0.y;
-        col[((staged + 3) & 15) * 32] = p0.x;
-        staged += 4;
-        p0 = p1;
-        p1 = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
-        ++cidx;
-      }
+    // Top up the ring: a round consumes at most 6 words.  The chunk stored now was requested
+    // at the previous top-up, so its latency is hidden unless the stream runs at > 8 bits/symbol.
+    while (staged - rd < 10) {
+      col[((staged + 0) & 15) * 32] = pf.w;
+      col[((staged + 1) & 15) * 32] = pf.z;
+      col[((staged + 2) & 15) * 32] = pf.y;
+      col[((staged + 3) & 15) * 32] = pf.x;
+      staged += 4;
+      pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
+      ++cidx;
     }
     const uint32_t target = left < 16 ? left : 16;
     while (cnt < target) {
-      const uint32_t code = __funnelshift_l(lo, hi, used) >> 20;
-      const uint32_t e = T[code];
-      used += e & 0xffu;
-      row[cnt] = (uint8_t)(e >> 8);
-      row[cnt + 1] = (uint8_t)(e >> 16);
-      cnt += (e >> 24) & 3u;
+      const uint32_t win = __funnelshift_l(lo, hi, used);
+      uint32_t e = T[win >> (32 - kDecBits)];
+      const uint32_t nb = (e >> 16) & 0xffu;
+      if (nb == 12 && (win & (1u << (31 - kDecBits)))) e = __byte_perm(e, 0, 0x3211);  // sibling 12-bit code
+      row[cnt] = (uint8_t)e;
+      row[cnt + 1] = (uint8_t)(e >> 8);
+      cnt += e >> 24;
+      used += nb;
       if (used >= 32) {
         hi = lo;
         lo = nx;
@@ -685,13 +707,13 @@ __global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict_
   }
   for (int i = threadIdx.x; i < num_syms; i += blockDim.x) sy[i] = syms[i];
   __syncthreads();
-  build_dtable(&bi, sy, T, threadIdx.x, blockDim.x);
+  build_dtable<kMaxCodeLen>(&bi, sy, T, threadIdx.x, blockDim.x);
   for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
-    const uint32_t v = T[e];
-    out[4 * e + 0] = (uint8_t)v;
-    out[4 * e + 1] = (uint8_t)(v >> 8);
-    out[4 * e + 2] = (uint8_t)(v >> 16);
-    out[4 * e + 3] = (uint8_t)((v >> 24) & 0xfu);
+    const uint32_t v = T[e];  // -> DecodedSym2x {num_bits_decoded, syms[2], num_syms} (:634-640)
+    out[4 * e + 0] = (uint8_t)(v >> 16);
+    out[4 * e + 1] = (uint8_t)v;
+    out[4 * e + 2] = (uint8_t)(v >> 8);
+    out[4 * e + 3] = (uint8_t)(v >> 24);
   }
 }
 
@@ -795,7 +817,7 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
 size_t decompress_smem_bytes(int K, int bpc) {
   const int nthreads = ((K * bpc + 31) / 32) * 32;
   const int nwarps = nthreads / 32;
-  size_t b = (size_t)bpc * 4096 * 4 + (size_t)nwarps * 16 * 32 * 4;
+  size_t b = (size_t)bpc * kDecEntries * 4 + (size_t)nwarps * 16 * 32 * 4;
   b += ((size_t)nthreads * 20 + 15) & ~(size_t)15;
   b += (size_t)bpc * sizeof(DecBlockInfo);
   return b;

@@ -7,7 +7,14 @@
 namespace hufb200 {
 
 constexpr int kHistThreads = 512;
-constexpr int kCompThreads = 512;
+#ifndef HUF_COMP_THREADS
+#define HUF_COMP_THREADS 256
+#endif
+#ifndef HUF_COMP_MINB
+#define HUF_COMP_MINB 4
+#endif
+constexpr int kCompThreads = HUF_COMP_THREADS;
+constexpr int kCompCtasPerSm = HUF_COMP_MINB;
 constexpr int kCompWarps = kCompThreads / 32;
 constexpr int kDecMaxThreads = 256;
 
