@@ -250,7 +250,7 @@ int hufb200_make_table(const uint32_t hist[256], uint16_t len_count[13], uint8_t
   if (len_mask) *len_mask = t.len_mask;
   for (int c = 0; c < 256; ++c) {
     const uint32_t e = t.enc[c];
-    const bool present = e != 0x40000000u;
+    const bool present = e != 0x10000000u;
     const uint32_t l = present ? (e >> 16) : 0;
     // BitCode.bits is left-aligned in 12 bits (codec/huffman.cpp:214-224)
     if (code_bits) code_bits[c] = present ? (uint16_t)((e & 0xffffu) << (HUFB200_MAX_CODE_LEN - l)) : 0;

@@ -13,7 +13,7 @@ namespace hufb200 {
 constexpr int kMaxCodeLen = 12;   // kMaxCodeLength, codec/huffman.cpp:38
 constexpr int kSlop = 8;          // kSlop, codec/huffman.cpp:770
 constexpr int kMaxK = 64;
-constexpr uint32_t kEncInvalid = 0x40000000u;  // enc[] entry of a symbol without a code
+constexpr uint32_t kEncInvalid = 0x10000000u;  // enc[] entry of a symbol without a code
 
 // Encode-side table.  Lives in shared memory (per-block tables) or in global
 // memory (shared-table mode, built by k_build_table).

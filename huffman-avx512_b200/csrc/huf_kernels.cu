@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(32) k_make_table(const uint32_t* __restrict__ 
 // ===========================================================================
 // Fused compress kernel: one CTA per block (CompressMulti<K>, codec/huffman.cpp:738-846)
 // ===========================================================================
-constexpr int kRingWords = 256;  // per-warp staging ring, in 32-bit stream words
+constexpr int kRingWords = 256;  // per-warp staging ring, in 32-bit stream words (1 KiB, 1 KiB-aligned)
 
 struct CompSmem {
   union {
@@ -153,6 +153,20 @@ __device__ __forceinline__ uint32_t shr_c(uint32_t x, uint32_t s) {
   asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
   return r;
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// byte i of w, zero-extended (one PRMT)
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
 
 // Loads the 16 symbols [off, off+16) of a slice as four little-endian words; symbols
 // beyond `valid` read as 0 and are masked by the caller.
@@ -165,10 +179,10 @@ __device__ __forceinline__ uint4 load16(const uint8_t* sp, uint32_t off, uint32_
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Sum of code lengths of the (up to) 4 symbols in w; `valid` symbols count.
-__device__ __forceinline__ uint32_t word_len(const uint32_t* enc, uint32_t w) {
-  return (enc[w & 0xffu] >> 16) + (enc[(w >> 8) & 0xffu] >> 16) + (enc[(w >> 16) & 0xffu] >> 16) +
-         (enc[w >> 24] >> 16);
+// Sum of the four entries of the symbols in w: code lengths add up in bits 16.., the low
+// halves (codes < 2^12) cannot carry into them.
+__device__ __forceinline__ uint32_t word_entries(const uint32_t* enc, uint32_t w) {
+  return enc[byte_of(w, 0)] + enc[byte_of(w, 1)] + enc[byte_of(w, 2)] + enc[byte_of(w, 3)];
 }
 
 // Per-stream bit total (the reference derives it from per-stream histograms, :776-782).
@@ -181,9 +195,11 @@ __device__ inline unsigned long long stream_length_warp(const uint32_t* enc, con
   const uint32_t full = sz & ~511u;
   for (uint32_t base = 0; base < full; base += 512) {
     const uint4 v = load16(sp, base + lane * 16, 16, aligned);
-    const uint32_t l = word_len(enc, v.x) + word_len(enc, v.y) + word_len(enc, v.z) + word_len(enc, v.w);
-    flag |= l;
-    acc += l;
+    // 16 entries: lengths <= 16*12 in bits 16..23, kEncInvalid entries pile up in bits 30+
+    const uint32_t s = ((word_entries(enc, v.x) >> 16) + (word_entries(enc, v.y) >> 16)) +
+                       ((word_entries(enc, v.z) >> 16) + (word_entries(enc, v.w) >> 16));
+    flag |= s;
+    acc += s;
   }
   if (full < sz) {
     const uint32_t off = full + lane * 16;
@@ -194,26 +210,32 @@ __device__ inline unsigned long long stream_length_warp(const uint32_t* enc, con
       acc += l;
     }
   }
-  if (flag & 0x7fffc000u) atomicOr(bad, 1u);  // a symbol without a code (kEncInvalid)
+  if (flag & 0xfffff000u) atomicOr(bad, 1u);  // a symbol without a code (kEncInvalid)
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
   return acc;
 }
 
-// ORs the `len` low bits of `code` (len <= 24) into the ring at stream bit position `pos`.
-__device__ __forceinline__ void ring_put(uint32_t* ring, uint32_t pos, uint32_t code, uint32_t len) {
+// ORs the `len` (<= 32) low bits of `code` into the warp's ring at stream bit position `pos`.
+// Bits of `code` above `len` are ignored.  ring_base: shared-space address, 1 KiB aligned.
+__device__ __forceinline__ void ring_put(uint32_t ring_base, uint32_t pos, uint32_t code, uint32_t len) {
   const uint32_t t = shl_c(code, 32u - len);  // left-aligned; len == 0 gives 0
   const uint32_t o = pos & 31u;
-  const uint32_t w = (pos >> 5) & (kRingWords - 1);
-  atomicOr(ring + w, t >> o);
-  atomicOr(ring + ((w + 1) & (kRingWords - 1)), shl_c(t, 32u - o));
+  const uint32_t a0 = ring_base | ((pos >> 3) & 0x3fcu);
+  const uint32_t a1 = ring_base | ((a0 + 4u) & 0x3fcu);
+  red_or_shared(a0, t >> o);
+  red_or_shared(a1, shl_c(t, 32u - o));
 }
 
-// Two table entries -> (code, len) of the pair, first symbol in the high bits.
-__device__ __forceinline__ void pair_code(uint32_t e0, uint32_t e1, uint32_t& code, uint32_t& len) {
-  const uint32_t l1 = e1 >> 16;
-  code = ((e0 & 0xffffu) << l1) | (e1 & 0xffffu);
-  len = (e0 >> 16) + l1;
+// Four table entries (first symbol first) -> the two pair codes and lengths.  c01 may carry
+// garbage above l01 bits (it always ends up left-aligned by a shift); c23 is clean.
+__device__ __forceinline__ void quad_code(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t& c01,
+                                          uint32_t& l01, uint32_t& c23, uint32_t& l23) {
+  const uint32_t l1 = e1 >> 16, l3 = e3 >> 16;
+  c01 = (e0 << l1) | (e1 & 0xffffu);
+  c23 = ((e2 & 0xffffu) << l3) | (e3 & 0xffffu);
+  l01 = (e0 + e1) >> 16;
+  l23 = (e2 + e3) >> 16;
 }
 
 // Encodes one stream (slice sp[0..sz)) whose region ends at byte offset e_off of dst and is
@@ -221,81 +243,93 @@ __device__ __forceinline__ void pair_code(uint32_t e0, uint32_t e1, uint32_t& co
 // whose first byte is the region's LAST byte; the first 8 bytes of the region stay zero).
 //
 // Stream word q (32 stream bits, MSB first) occupies bytes e_off-4q-4 .. e_off-4q-1 as a
-// little-endian u32.  With r = e_off & 3 the aligned output word number m at dst + (e_off-r) - 4m
-// equals funnelshift_l(W[m], W[m-1], 8r) (W[-1] = 0), so the warp emits aligned 128-byte rows.
-__device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t* ring, const uint8_t* sp,
+// little-endian u32.  With r = ((e_off-1) & 3) + 1 (1..4) the aligned output word number m at
+// dst + (e_off - r) - 4m equals the top half of (W[m-1]:W[m]) << 8r (W[-1] = 0), so the warp
+// emits aligned 128-byte rows; complete stream words leave the ring 32 at a time.
+__device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_base, const uint8_t* sp,
                                           uint32_t sz, unsigned long long bits, uint8_t* dst,
                                           uint32_t e_off, uint32_t region) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
-  const uint32_t r = e_off & 3u;
+  const uint32_t r = ((e_off - 1u) & 3u) + 1u;
+  const uint32_t sh = 8u * r;
   const uint32_t e_al = e_off - r;
-  const uint32_t s_off = e_off - region;
-  const uint32_t s_al = (s_off + 3u) & ~3u;
-  const uint32_t m_first = r ? 0u : 1u;
+  const uint32_t s_al = (e_off - region + 3u) & ~3u;
   const uint32_t m_last = (e_al - s_al) >> 2;  // inclusive
-  uint32_t* out_words = reinterpret_cast<uint32_t*>(dst + e_al);  // word m at out_words[-m]
+  uint32_t* out_lane = reinterpret_cast<uint32_t*>(dst + e_al) - lane;  // word m at out_lane[lane - m]
+  const uint32_t ring_lane = ring_base + 4u * (uint32_t)lane;
 
   unsigned long long bitpos = 0;
-  uint32_t m_next = m_first;
+  uint32_t m_next = 0;  // next output word to write
+  uint32_t carry = 0;   // W[m_next - 1]
   for (uint32_t base = 0; base < sz; base += 512) {
     const uint32_t off = base + lane * 16;
     const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
     const uint4 v = load16(sp, off, valid, aligned);
-    uint32_t code[8], len[8];
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t c01[4], l01[4], c23[4], l23[4];
     if (valid == 16) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        pair_code(enc[w[j] & 0xffu], enc[(w[j] >> 8) & 0xffu], code[2 * j], len[2 * j]);
-        pair_code(enc[(w[j] >> 16) & 0xffu], enc[w[j] >> 24], code[2 * j + 1], len[2 * j + 1]);
-      }
+      for (int j = 0; j < 4; ++j)
+        quad_code(enc[byte_of(w[j], 0)], enc[byte_of(w[j], 1)], enc[byte_of(w[j], 2)], enc[byte_of(w[j], 3)],
+                  c01[j], l01[j], c23[j], l23[j]);
     } else {  // last iteration of the slice: symbols past its end contribute no bits
 #pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        const uint32_t b0 = (w[p >> 1] >> (16 * (p & 1))) & 0xffu;
-        const uint32_t b1 = (w[p >> 1] >> (16 * (p & 1) + 8)) & 0xffu;
-        const uint32_t e0 = (uint32_t)(2 * p) < valid ? enc[b0] : 0u;
-        const uint32_t e1 = (uint32_t)(2 * p + 1) < valid ? enc[b1] : 0u;
-        pair_code(e0, e1, code[p], len[p]);
+      for (int j = 0; j < 4; ++j) {
+        uint32_t e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = (uint32_t)(4 * j + i) < valid ? enc[byte_of(w[j], i)] : 0u;
+        quad_code(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
       }
     }
-    uint32_t lane_len = 0;
+    uint32_t lq[4];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) lane_len += len[p];
+    for (int j = 0; j < 4; ++j) lq[j] = l01[j] + l23[j];
+    const uint32_t lane_len = (lq[0] + lq[1]) + (lq[2] + lq[3]);
     const uint32_t incl = warp_incl_scan(lane_len);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t pos = (uint32_t)(bitpos & 0xffffffffu) + (incl - lane_len);  // only low bits matter
+    uint32_t pos = (uint32_t)bitpos + (incl - lane_len);  // only the low bits matter
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      ring_put(ring, pos, code[p], len[p]);
-      pos += len[p];
+    for (int j = 0; j < 4; ++j) {
+      if (lq[j] <= 32) {  // almost always: one put for four symbols
+        ring_put(ring_base, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
+      } else {
+        ring_put(ring_base, pos, c01[j], l01[j]);
+        ring_put(ring_base, pos + l01[j], c23[j], l23[j]);
+      }
+      pos += lq[j];
     }
     bitpos += total;
     __syncwarp();
-    // flush the complete stream words
+    // move complete stream words out of the ring, 32 at a time
     const uint32_t wc = (uint32_t)(bitpos >> 5);
-    for (uint32_t m = m_next + lane; m < wc; m += 32) {
-      const uint32_t hi = m ? ring[(m - 1) & (kRingWords - 1)] : 0u;
-      const uint32_t lo = ring[m & (kRingWords - 1)];
-      out_words[-(long)m] = __funnelshift_l(lo, hi, 8 * r);
-    }
-    __syncwarp();
-    if (wc > m_next) {
-      for (uint32_t j = (m_next ? m_next - 1 : 0u) + lane; j + 1 < wc; j += 32) ring[j & (kRingWords - 1)] = 0;
-      m_next = wc;
+    while (wc - m_next >= 32) {
+      const uint32_t a = ring_lane + ((m_next << 2) & 0x3fcu);  // lanes wrap together (m_next % 32 == 0)
+      const uint32_t lo = lds_u32(a);
+      sts_u32(a, 0);
+      uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
+      if (lane == 0) hi = carry;
+      carry = __shfl_sync(0xffffffffu, lo, 31);
+      *(out_lane - m_next) = __funnelshift_lc(lo, hi, sh);
+      m_next += 32;
     }
     __syncwarp();
   }
-  // tail: partial word, padding and the zero slop below the stream
+  // tail: remaining complete words, the partial word, padding and the zero slop below the stream
   const uint32_t wtot = (uint32_t)((bits + 31) >> 5);
-  for (uint32_t m = m_next + lane; m <= m_last; m += 32) {
-    const uint32_t hi = (m >= 1 && m - 1 < wtot) ? ring[(m - 1) & (kRingWords - 1)] : 0u;
-    const uint32_t lo = (m < wtot) ? ring[m & (kRingWords - 1)] : 0u;
-    out_words[-(long)m] = __funnelshift_l(lo, hi, 8 * r);
+  for (; m_next <= m_last; m_next += 32) {
+    const uint32_t m = m_next + lane;
+    uint32_t lo = 0;
+    if (m < wtot) {
+      const uint32_t a = ring_base + ((m << 2) & 0x3fcu);
+      lo = lds_u32(a);
+      sts_u32(a, 0);
+    }
+    uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
+    if (lane == 0) hi = carry;
+    carry = __shfl_sync(0xffffffffu, lo, 31);
+    if (m <= m_last) *(out_lane - m_next) = __funnelshift_lc(lo, hi, sh);
   }
-  __syncwarp();
-  for (int j = lane; j < kRingWords; j += 32) ring[j] = 0;
   __syncwarp();
 }
 
@@ -304,7 +338,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
                   uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
                   uint32_t* __restrict__ comp_sizes, const HufTable* __restrict__ shared_tab,
                   int check_presence, uint32_t* __restrict__ status) {
-  __shared__ CompSmem sm;
+  __shared__ __align__(1024) CompSmem sm;
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -409,7 +443,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       slice_geom(bn, K, s, st, sz);
       const uint32_t e_off = hdr_total + sm.region_end[s];
       const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
-      encode_stream_warp(sm.tab.enc, sm.u.ring[warp], src + st, sz, sm.stream_bits[s], dst, e_off, region);
+      encode_stream_warp(sm.tab.enc, smem_u32(&sm.u.ring[warp][0]), src + st, sz, sm.stream_bits[s], dst, e_off, region);
     }
     __syncthreads();
   }
