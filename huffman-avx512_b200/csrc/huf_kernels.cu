@@ -465,59 +465,61 @@ struct DecBlockInfo {
   uint32_t first_idx[16];  // index into sorted_syms of the first code of each length
 };
 
-// Decode table over the next BITS bits of the stream (Decoder2x, codec/huffman.cpp:642-704).
-// Entry: byte0 = sym0, byte1 = sym1, byte2 = bits consumed, byte3 = number of symbols (1 or 2).
-//   BITS = 12: exactly the reference's two-symbol table (pair taken iff l1 + l2 <= 12, :653).
-//   BITS = 11: what the decode kernel uses (8 KiB instead of 16 KiB per block doubles the
-//   resident warps).  A 12-bit code cannot be resolved by 11 bits, but 12-bit codes come in
-//   sibling pairs that share their first 11 bits (the code is complete), so such an entry
-//   carries both candidates (sym0 for next bit 0, sym1 for next bit 1), bits = 12, 1 symbol;
-//   pairs are taken iff l1 + l2 <= 11.
-// During construction bits 26..29 of an entry hold the first code's own length.
-template <int BITS>
-__device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, int tid,
-                                    int nthreads) {
+// Decode table over the next BITS bits of the stream, up to MAXSYM symbols per entry
+// (generalises Decoder2x, codec/huffman.cpp:642-704).
+//   entry: byte0..2 = symbols, bits 24..27 = stream bits consumed, bits 30..31 = symbol count.
+//   BITS = 12, MAXSYM = 2: exactly the reference's two-symbol table (pair iff l1+l2 <= 12, :653).
+//   BITS = 11, MAXSYM = 3: what the decode kernel uses -- 8 KiB instead of 16 KiB per block
+//     doubles the resident warps, the third symbol cuts the lookups per symbol.  A 12-bit code
+//     cannot be resolved by 11 bits, but 12-bit codes come in sibling pairs sharing their first
+//     11 bits (the code is complete), so such an entry holds both candidates (byte0 for next
+//     bit 0, byte1 for next bit 1) with symbol count 0 as the marker.
+// T1 (u16 per entry, sym | len << 8) is scratch that may be reused afterwards.
+template <int BITS, int MAXSYM>
+__device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, uint16_t* T1,
+                                    int tid, int nthreads) {
   constexpr int N = 1 << BITS;
   constexpr int SH = kMaxCodeLen - BITS;
   for (int e = tid; e < N; e += nthreads) {
     const uint32_t v = (uint32_t)e << SH;  // left-aligned 12-bit value of this prefix
     int l = 0;
     while (l <= BITS && v >= bi->code_end[l]) ++l;
-    uint32_t ent;
     if (l <= BITS) {
       const uint32_t lo = l ? bi->code_end[l - 1] : 0u;
       const uint32_t idx = bi->first_idx[l] + ((v - lo) >> (kMaxCodeLen - l));
       const uint32_t sym = idx < bi->num_syms ? syms[idx] : 0u;
-      ent = sym | ((uint32_t)l << 16) | (1u << 24) | ((uint32_t)l << 26);
-    } else if (BITS < kMaxCodeLen && v < bi->code_end[kMaxCodeLen]) {
-      const uint32_t idx = bi->first_idx[kMaxCodeLen] + (v - bi->code_end[kMaxCodeLen - 1]);
-      const uint32_t s0 = idx < bi->num_syms ? syms[idx] : 0u;
-      const uint32_t s1 = idx + 1 < bi->num_syms ? syms[idx + 1] : 0u;
-      ent = s0 | (s1 << 8) | (12u << 16) | (1u << 24) | (12u << 26);
+      T1[e] = (uint16_t)(sym | ((uint32_t)l << 8));
     } else {
-      ent = (12u << 16) | (1u << 24) | (12u << 26);  // not covered by any code (malformed table)
+      T1[e] = 0xff00u;  // never fits behind another symbol
+      uint32_t ent = 12u << 24;  // symbol count 0: sibling pair of 12-bit codes (or malformed table)
+      if (BITS < kMaxCodeLen && v < bi->code_end[kMaxCodeLen]) {
+        const uint32_t idx = bi->first_idx[kMaxCodeLen] + (v - bi->code_end[kMaxCodeLen - 1]);
+        ent |= (idx < bi->num_syms ? syms[idx] : 0u) | ((idx + 1 < bi->num_syms ? syms[idx + 1] : 0u) << 8);
+      }
+      T[e] = ent;
     }
-    T[e] = ent;
   }
   __syncthreads();
   for (int e = tid; e < N; e += nthreads) {
-    const uint32_t e1 = T[e];
-    const uint32_t l1 = (e1 >> 26) & 15u;
-    if (l1 <= (uint32_t)BITS) {
-      const uint32_t rest = ((uint32_t)e << l1) & (uint32_t)(N - 1);
-      const uint32_t e2 = T[rest];  // sym0 / own-length fields are never rewritten
-      const uint32_t l2 = (e2 >> 26) & 15u;
-      if (l1 + l2 <= (uint32_t)BITS)  // :653
-        T[e] = (e1 & 0xffu) | ((e2 & 0xffu) << 8) | ((l1 + l2) << 16) | (2u << 24) | (l1 << 26);
+    const uint32_t t = T1[e];
+    if ((t >> 8) > (uint32_t)BITS) continue;  // written above
+    uint32_t nb = t >> 8, n = 1, out = t & 0xffu;
+#pragma unroll
+    for (int k = 1; k < MAXSYM; ++k) {
+      const uint32_t t2 = T1[((uint32_t)e << nb) & (uint32_t)(N - 1)];
+      if (nb + (t2 >> 8) > (uint32_t)BITS) break;  // :653
+      out |= (t2 & 0xffu) << (8 * k);
+      nb += t2 >> 8;
+      ++n;
     }
+    T[e] = out | (nb << 24) | (n << 30);
   }
-  __syncthreads();
-  for (int e = tid; e < N; e += nthreads) T[e] &= 0x03ffffffu;
   __syncthreads();
 }
 
 constexpr int kDecBits = 11;
 constexpr int kDecEntries = 1 << kDecBits;
+constexpr int kDecRow = 20;  // bytes of output staging per lane: 16 per round + 2 spill-over
 
 __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
                                     DecBlockInfo* bi) {
@@ -560,6 +562,21 @@ __device__ __forceinline__ uint4 ld_chunk(uintptr_t addr, uintptr_t lo_lim) {
   if (addr >= lo_lim) return *reinterpret_cast<const uint4*>(addr);
   return make_uint4(0, 0, 0, 0);
 }
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// per-CTA scratch behind the tables: the T1 build scratch, later the lane rings and output rows
+__host__ __device__ inline size_t dec_region_bytes(int bpc, int nthreads) {
+  const size_t a = (size_t)bpc * kDecEntries * 2;
+  const size_t b = (size_t)(nthreads >> 5) * 16 * 32 * 4 + (((size_t)nthreads * kDecRow + 15) & ~(size_t)15);
+  return ((a > b ? a : b) + 15) & ~(size_t)15;
+}
 
 __global__ void __launch_bounds__(kDecMaxThreads)
 k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* __restrict__ offsets,
@@ -567,13 +584,12 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
                     uint8_t* __restrict__ raw, uint64_t raw_n, uint32_t block_size,
                     uint32_t* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  // layout: tables [bpc][2048] u32 | rings [nwarps][16][32] u32 | rows [nthreads][20] u8 | infos [bpc]
+  // layout: tables [bpc][2048] u32 | region (T1 scratch, then rings [nwarps][16][32] u32 + rows) | infos [bpc]
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
   uint32_t* tables = reinterpret_cast<uint32_t*>(dsm);
-  uint32_t* rings = tables + (size_t)bpc * kDecEntries;
-  uint8_t* rows = reinterpret_cast<uint8_t*>(rings + (size_t)nwarps * 16 * 32);
-  DecBlockInfo* infos = reinterpret_cast<DecBlockInfo*>(rows + (((size_t)nthreads * 20 + 15) & ~(size_t)15));
+  uint8_t* region = dsm + (size_t)bpc * kDecEntries * 4;
+  DecBlockInfo* infos = reinterpret_cast<DecBlockInfo*>(region + dec_region_bytes(bpc, nthreads));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -593,11 +609,12 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     }
   }
   __syncthreads();
-  // ---- two-symbol tables
+  // ---- decode tables
   for (int lb = 0; lb < bpc; ++lb) {
     const DecBlockInfo* bi = &infos[lb];
     if (b0 + lb < n_blocks && bi->ok && bi->raw_size != 0) {
-      build_dtable<kDecBits>(bi, comp + offsets[b0 + lb] + bi->syms_off, tables + (size_t)lb * kDecEntries, tid, nthreads);
+      build_dtable<kDecBits, 3>(bi, comp + offsets[b0 + lb] + bi->syms_off, tables + (size_t)lb * kDecEntries,
+                                reinterpret_cast<uint16_t*>(region) + (size_t)lb * kDecEntries, tid, nthreads);
     }
   }
   __syncthreads();
@@ -613,7 +630,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t left = 0;           // symbols still to produce
   uint8_t* outp = nullptr;     // next output byte
   uintptr_t e16 = 16, lo_lim = 0;
-  uint32_t used = 0;           // bits consumed from hi
+  uint32_t acc = 0;            // bits 0..5: bits consumed from the window, bits 6..: symbols in the row
   uint32_t rd = 0, staged = 0, cidx = 0;
   bool bad_lane = false;
   if (active) {
@@ -638,13 +655,17 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     const uint32_t pad = (uint32_t)(e16 - end_addr);
     lo_lim = (uintptr_t)blk & ~(uintptr_t)15;
     rd = pad >> 2;
-    used = 8 * (pad & 3);
+    acc = 8 * (pad & 3);
   }
   if (bad_lane && status) atomicOr(status, 1u);
 
-  const uint32_t* T = tables + (size_t)(lb < bpc ? lb : 0) * kDecEntries;
-  uint32_t* col = rings + (size_t)warp * 16 * 32 + lane;  // word i at col[(i & 15) * 32]
-  uint8_t* row = rows + (size_t)tid * 20;
+  // shared-space addresses, kept in registers
+  const uint32_t t_addr = smem_u32(tables + (size_t)(lb < bpc ? lb : 0) * kDecEntries);
+  const uint32_t col = smem_u32(region) + (uint32_t)warp * (16 * 32 * 4) + 4u * (uint32_t)lane;  // word i at col + (i & 15) * 128
+  const uint32_t row = smem_u32(region) + (uint32_t)nwarps * (16 * 32 * 4) + (uint32_t)tid * kDecRow;
+  // make the three addresses opaque so that they stay in registers instead of being recomputed
+  // from tid / %ctaid inside the lookup loop
+  asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
 
   // prime: stage 3 chunks (12 words) and keep the next one in registers
   uint4 pf;
@@ -652,81 +673,90 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const uint4 ch = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
-      col[((staged + 0) & 15) * 32] = ch.w;
-      col[((staged + 1) & 15) * 32] = ch.z;
-      col[((staged + 2) & 15) * 32] = ch.y;
-      col[((staged + 3) & 15) * 32] = ch.x;
+      sts_u32(col + ((staged + 0) & 15) * 128, ch.w);
+      sts_u32(col + ((staged + 1) & 15) * 128, ch.z);
+      sts_u32(col + ((staged + 2) & 15) * 128, ch.y);
+      sts_u32(col + ((staged + 3) & 15) * 128, ch.x);
       staged += 4;
       ++cidx;
     }
     pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
     ++cidx;
   }
-  uint32_t hi = col[(rd & 15) * 32];
-  uint32_t lo = col[((rd + 1) & 15) * 32];
-  uint32_t nx = col[((rd + 2) & 15) * 32];
+  uint32_t hi = lds_u32(col + (rd & 15) * 128);
+  uint32_t lo = lds_u32(col + ((rd + 1) & 15) * 128);
+  uint32_t nx = lds_u32(col + ((rd + 2) & 15) * 128);
   rd += 3;
 
-  uint32_t cnt = 0;  // symbols already sitting in row[] (0 or 1 carried over)
   const uint32_t max_left = __reduce_max_sync(0xffffffffu, left);
   for (uint32_t round = 0; round * 16 < max_left; ++round) {
-    // Top up the ring: a round consumes at most 6 words.  The chunk stored now was requested
+    // Top up the ring: a round consumes at most 7 words.  The chunk stored now was requested
     // at the previous top-up, so its latency is hidden unless the stream runs at > 8 bits/symbol.
-    while (staged - rd < 10) {
-      col[((staged + 0) & 15) * 32] = pf.w;
-      col[((staged + 1) & 15) * 32] = pf.z;
-      col[((staged + 2) & 15) * 32] = pf.y;
-      col[((staged + 3) & 15) * 32] = pf.x;
+    while (staged - rd < 11) {
+      const uint32_t o = (staged & 15) * 128;  // staged % 4 == 0: the four words do not wrap
+      sts_u32(col + o, pf.w);
+      sts_u32(col + o + 128, pf.z);
+      sts_u32(col + o + 256, pf.y);
+      sts_u32(col + o + 384, pf.x);
       staged += 4;
       pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
       ++cidx;
     }
     const uint32_t target = left < 16 ? left : 16;
-    while (cnt < target) {
-      const uint32_t win = __funnelshift_l(lo, hi, used);
-      uint32_t e = T[win >> (32 - kDecBits)];
-      const uint32_t nb = (e >> 16) & 0xffu;
-      if (nb == 12 && (win & (1u << (31 - kDecBits)))) e = __byte_perm(e, 0, 0x3211);  // sibling 12-bit code
-      row[cnt] = (uint8_t)e;
-      row[cnt + 1] = (uint8_t)(e >> 8);
-      cnt += e >> 24;
-      used += nb;
-      if (used >= 32) {
+    const uint32_t limit = target << 6;
+    uint32_t rdo = (rd & 15) * 128;
+    while (acc < limit) {
+      const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
+      uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
+      if (e < (1u << 30)) {  // sibling pair of 12-bit codes: the next bit picks the symbol
+        if (win & (1u << (31 - kDecBits))) e >>= 8;
+        e = (e & 0xffu) | (12u << 24) | (1u << 30);
+      }
+      const uint32_t wr = row + (acc >> 6);
+      sts_u8(wr, e);
+      sts_u8(wr + 1, e >> 8);
+      sts_u8(wr + 2, e >> 16);
+      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..
+      if (acc & 32u) {
         hi = lo;
         lo = nx;
-        nx = col[(rd & 15) * 32];
+        nx = lds_u32(col + rdo);
+        rdo = (rdo + 128) & (15 * 128);
         ++rd;
-        used -= 32;
+        acc -= 32;
       }
     }
     if (target) {
       if (target == 16 && (((uintptr_t)outp) & 15) == 0) {
         uint4 v;
-        v.x = *reinterpret_cast<const uint32_t*>(row + 0);
-        v.y = *reinterpret_cast<const uint32_t*>(row + 4);
-        v.z = *reinterpret_cast<const uint32_t*>(row + 8);
-        v.w = *reinterpret_cast<const uint32_t*>(row + 12);
+        v.x = lds_u32(row + 0);
+        v.y = lds_u32(row + 4);
+        v.z = lds_u32(row + 8);
+        v.w = lds_u32(row + 12);
         *reinterpret_cast<uint4*>(outp) = v;
       } else {
-        for (uint32_t i = 0; i < target; ++i) outp[i] = row[i];
+        for (uint32_t i = 0; i < target; ++i) outp[i] = (uint8_t)lds_u8(row + i);
       }
       outp += target;
       left -= target;
-      if (cnt > target) {  // second symbol of the last pair belongs to the next round
-        row[0] = row[target];
-        cnt = 1;
-      } else {
-        cnt = 0;
+      // symbols decoded beyond this round's 16 (at most 2) open the next round
+      const uint32_t extra = (acc >> 6) - target;
+      if (extra) {
+        sts_u8(row + 0, lds_u8(row + target));
+        sts_u8(row + 1, lds_u8(row + target + 1));
       }
+      acc = (acc & 63u) | (extra << 6);
     }
   }
 }
 
-// Dumps the decode kernel's two-symbol table in the reference's DecodedSym2x layout.
+// Dumps the reference-format two-symbol table (BITS = 12, 2 symbols) built by the decode
+// kernel's builder: DecodedSym2x {num_bits_decoded, syms[2], num_syms} (:634-640).
 __global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict__ len_count,
                                                      const uint8_t* __restrict__ syms, int num_syms,
                                                      uint8_t* __restrict__ out) {
   __shared__ uint32_t T[4096];
+  __shared__ uint16_t T1[4096];
   __shared__ DecBlockInfo bi;
   __shared__ uint8_t sy[256];
   if (threadIdx.x == 0) {
@@ -741,13 +771,13 @@ __global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict_
   }
   for (int i = threadIdx.x; i < num_syms; i += blockDim.x) sy[i] = syms[i];
   __syncthreads();
-  build_dtable<kMaxCodeLen>(&bi, sy, T, threadIdx.x, blockDim.x);
+  build_dtable<kMaxCodeLen, 2>(&bi, sy, T, T1, threadIdx.x, blockDim.x);
   for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
-    const uint32_t v = T[e];  // -> DecodedSym2x {num_bits_decoded, syms[2], num_syms} (:634-640)
-    out[4 * e + 0] = (uint8_t)(v >> 16);
+    const uint32_t v = T[e];
+    out[4 * e + 0] = (uint8_t)((v >> 24) & 15u);
     out[4 * e + 1] = (uint8_t)v;
     out[4 * e + 2] = (uint8_t)(v >> 8);
-    out[4 * e + 3] = (uint8_t)(v >> 24);
+    out[4 * e + 3] = (uint8_t)(v >> 30);
   }
 }
 
@@ -850,11 +880,7 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
 
 size_t decompress_smem_bytes(int K, int bpc) {
   const int nthreads = ((K * bpc + 31) / 32) * 32;
-  const int nwarps = nthreads / 32;
-  size_t b = (size_t)bpc * kDecEntries * 4 + (size_t)nwarps * 16 * 32 * 4;
-  b += ((size_t)nthreads * 20 + 15) & ~(size_t)15;
-  b += (size_t)bpc * sizeof(DecBlockInfo);
-  return b;
+  return (size_t)bpc * kDecEntries * 4 + dec_region_bytes(bpc, nthreads) + (size_t)bpc * sizeof(DecBlockInfo);
 }
 
 cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
