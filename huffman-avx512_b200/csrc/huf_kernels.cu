@@ -474,9 +474,10 @@ struct DecBlockInfo {
 //     cannot be resolved by 11 bits, but 12-bit codes come in sibling pairs sharing their first
 //     11 bits (the code is complete), so such an entry holds both candidates (byte0 for next
 //     bit 0, byte1 for next bit 1) with symbol count 0 as the marker.
-// T1 (u16 per entry, sym | len << 8) is scratch that may be reused afterwards.
+// L1 (u8 per entry: the first code's own length, 15 = none) is scratch that may be reused
+// afterwards; the first symbol sits in byte 0 of T from the first pass on and never changes.
 template <int BITS, int MAXSYM>
-__device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, uint16_t* T1,
+__device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, uint8_t* L1,
                                     int tid, int nthreads) {
   constexpr int N = 1 << BITS;
   constexpr int SH = kMaxCodeLen - BITS;
@@ -487,11 +488,12 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
     if (l <= BITS) {
       const uint32_t lo = l ? bi->code_end[l - 1] : 0u;
       const uint32_t idx = bi->first_idx[l] + ((v - lo) >> (kMaxCodeLen - l));
-      const uint32_t sym = idx < bi->num_syms ? syms[idx] : 0u;
-      T1[e] = (uint16_t)(sym | ((uint32_t)l << 8));
+      T[e] = idx < bi->num_syms ? syms[idx] : 0u;
+      L1[e] = (uint8_t)l;
     } else {
-      T1[e] = 0xff00u;  // never fits behind another symbol
-      uint32_t ent = 12u << 24;  // symbol count 0: sibling pair of 12-bit codes (or malformed table)
+      L1[e] = 15;  // never fits behind another symbol
+      // sibling pair of 12-bit codes (or a malformed table): one symbol, 12 bits, both candidates
+      uint32_t ent = (12u << 24) | (1u << 30);
       if (BITS < kMaxCodeLen && v < bi->code_end[kMaxCodeLen]) {
         const uint32_t idx = bi->first_idx[kMaxCodeLen] + (v - bi->code_end[kMaxCodeLen - 1]);
         ent |= (idx < bi->num_syms ? syms[idx] : 0u) | ((idx + 1 < bi->num_syms ? syms[idx + 1] : 0u) << 8);
@@ -501,15 +503,16 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
   }
   __syncthreads();
   for (int e = tid; e < N; e += nthreads) {
-    const uint32_t t = T1[e];
-    if ((t >> 8) > (uint32_t)BITS) continue;  // written above
-    uint32_t nb = t >> 8, n = 1, out = t & 0xffu;
+    uint32_t nb = L1[e];
+    if (nb > (uint32_t)BITS) continue;  // written above
+    uint32_t n = 1, out = T[e] & 0xffu;
 #pragma unroll
     for (int k = 1; k < MAXSYM; ++k) {
-      const uint32_t t2 = T1[((uint32_t)e << nb) & (uint32_t)(N - 1)];
-      if (nb + (t2 >> 8) > (uint32_t)BITS) break;  // :653
-      out |= (t2 & 0xffu) << (8 * k);
-      nb += t2 >> 8;
+      const uint32_t rest = ((uint32_t)e << nb) & (uint32_t)(N - 1);
+      const uint32_t l2 = L1[rest];
+      if (nb + l2 > (uint32_t)BITS) break;  // :653
+      out |= (T[rest] & 0xffu) << (8 * k);  // byte 0 is stable under concurrent rewrites
+      nb += l2;
       ++n;
     }
     T[e] = out | (nb << 24) | (n << 30);
@@ -573,7 +576,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 
 // per-CTA scratch behind the tables: the T1 build scratch, later the lane rings and output rows
 __host__ __device__ inline size_t dec_region_bytes(int bpc, int nthreads) {
-  const size_t a = (size_t)bpc * kDecEntries * 2;
+  const size_t a = (size_t)bpc * kDecEntries;
   const size_t b = (size_t)(nthreads >> 5) * 16 * 32 * 4 + (((size_t)nthreads * kDecRow + 15) & ~(size_t)15);
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
@@ -614,7 +617,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     const DecBlockInfo* bi = &infos[lb];
     if (b0 + lb < n_blocks && bi->ok && bi->raw_size != 0) {
       build_dtable<kDecBits, 3>(bi, comp + offsets[b0 + lb] + bi->syms_off, tables + (size_t)lb * kDecEntries,
-                                reinterpret_cast<uint16_t*>(region) + (size_t)lb * kDecEntries, tid, nthreads);
+                                region + (size_t)lb * kDecEntries, tid, nthreads);
     }
   }
   __syncthreads();
@@ -708,15 +711,13 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     while (acc < limit) {
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
       uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
-      if (e < (1u << 30)) {  // sibling pair of 12-bit codes: the next bit picks the symbol
-        if (win & (1u << (31 - kDecBits))) e >>= 8;
-        e = (e & 0xffu) | (12u << 24) | (1u << 30);
-      }
       const uint32_t wr = row + (acc >> 6);
+      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6.. (the only loop-carried chain)
+      // a 12-bit code: the entry holds both siblings, the next bit picks one (off the critical chain)
+      if ((e & (15u << 24)) == (12u << 24) && (win & (1u << (31 - kDecBits)))) e >>= 8;
       sts_u8(wr, e);
       sts_u8(wr + 1, e >> 8);
       sts_u8(wr + 2, e >> 16);
-      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..
       if (acc & 32u) {
         hi = lo;
         lo = nx;
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict_
                                                      const uint8_t* __restrict__ syms, int num_syms,
                                                      uint8_t* __restrict__ out) {
   __shared__ uint32_t T[4096];
-  __shared__ uint16_t T1[4096];
+  __shared__ uint8_t T1[4096];
   __shared__ DecBlockInfo bi;
   __shared__ uint8_t sy[256];
   if (threadIdx.x == 0) {
