@@ -100,11 +100,13 @@ constexpr size_t kMaxBlock = (size_t)1 << 30;  // offsets are 32-bit inside a bu
 constexpr uint32_t kMagic = 0x32424648u;        // "HFB2"
 constexpr size_t kContainerHeader = 32;
 
-// blocks per decode CTA: fill whole warps with K-lane groups where K divides 32
+// Blocks per decode CTA: about 128 lanes (4 warps) per CTA so that the per-CTA shared-memory
+// reserve is amortised, capped so that the tables stay within the default 48 KiB.
 int decode_bpc(int k) {
-  if (k >= 32) return (k % 32 == 0) ? 1 : (k == 48 ? 2 : 1);
-  int bpc = 32 / k;
-  return bpc < 1 ? 1 : (bpc > 8 ? 8 : bpc);
+  int bpc = 128 / k;
+  if (bpc < 1) bpc = 1;
+  if (bpc > 16) bpc = 16;
+  return bpc;
 }
 
 int compress_grid(uint32_t n_blocks, int sms) {

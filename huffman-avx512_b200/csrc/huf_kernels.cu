@@ -463,17 +463,17 @@ struct DecBlockInfo {
   uint32_t num_syms;
   uint32_t code_end[16];   // left-aligned (12-bit) end of the code range of each length
   uint32_t first_idx[16];  // index into sorted_syms of the first code of each length
+  uint8_t syms[256];       // sorted_syms, for the codes longer than the table's index
 };
 
 // Decode table over the next BITS bits of the stream, up to MAXSYM symbols per entry
 // (generalises Decoder2x, codec/huffman.cpp:642-704).
 //   entry: byte0..2 = symbols, bits 24..27 = stream bits consumed, bits 30..31 = symbol count.
 //   BITS = 12, MAXSYM = 2: exactly the reference's two-symbol table (pair iff l1+l2 <= 12, :653).
-//   BITS = 11, MAXSYM = 3: what the decode kernel uses -- 8 KiB instead of 16 KiB per block
-//     doubles the resident warps, the third symbol cuts the lookups per symbol.  A 12-bit code
-//     cannot be resolved by 11 bits, but 12-bit codes come in sibling pairs sharing their first
-//     11 bits (the code is complete), so such an entry holds both candidates (byte0 for next
-//     bit 0, byte1 for next bit 1) with symbol count 0 as the marker.
+//   BITS = kDecBits (11), MAXSYM = 3: what the decode kernel uses: three symbols per lookup cut
+//     the lookups (the kernel is bound by shared-memory wavefronts), 8 KiB instead of 16 KiB per
+//     block keeps enough warps resident; a prefix that belongs to a code longer than BITS gets
+//     symbol count 0 and is resolved arithmetically from the canonical code ranges (escape_decode).
 // L1 (u8 per entry: the first code's own length, 15 = none) is scratch that may be reused
 // afterwards; the first symbol sits in byte 0 of T from the first pass on and never changes.
 template <int BITS, int MAXSYM>
@@ -492,13 +492,7 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
       L1[e] = (uint8_t)l;
     } else {
       L1[e] = 15;  // never fits behind another symbol
-      // sibling pair of 12-bit codes (or a malformed table): one symbol, 12 bits, both candidates
-      uint32_t ent = (12u << 24) | (1u << 30);
-      if (BITS < kMaxCodeLen && v < bi->code_end[kMaxCodeLen]) {
-        const uint32_t idx = bi->first_idx[kMaxCodeLen] + (v - bi->code_end[kMaxCodeLen - 1]);
-        ent |= (idx < bi->num_syms ? syms[idx] : 0u) | ((idx + 1 < bi->num_syms ? syms[idx + 1] : 0u) << 8);
-      }
-      T[e] = ent;
+      T[e] = 0;    // symbol count 0: code longer than BITS (or a malformed table) -> escape
     }
   }
   __syncthreads();
@@ -520,7 +514,10 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
   __syncthreads();
 }
 
-constexpr int kDecBits = 11;
+#ifndef HUF_DEC_BITS
+#define HUF_DEC_BITS 11
+#endif
+constexpr int kDecBits = HUF_DEC_BITS;
 constexpr int kDecEntries = 1 << kDecBits;
 constexpr int kDecRow = 20;  // bytes of output staging per lane: 16 per round + 2 spill-over
 
@@ -558,7 +555,19 @@ __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int 
   bi->ends_off = pos + nsyms;
   bi->payload_off = pos + nsyms + 4u * (uint32_t)(K - 1);
   if (bi->payload_off > comp_size) return;
+  for (uint32_t i = 0; i < nsyms; ++i) bi->syms[i] = blk[pos + i];
   bi->ok = 1;
+}
+
+// One symbol whose code is longer than the table index: canonical codes of length l occupy
+// [code_end[l-1], code_end[l]) of the left-aligned 12-bit code space in sorted_syms order
+// (ForallCodes, codec/huffman.cpp:260-284).  Returns a table-format entry.
+__device__ __forceinline__ uint32_t escape_decode(const DecBlockInfo* bi, uint32_t win) {
+  const uint32_t w12 = win >> 20;
+  int l = kDecBits + 1;
+  while (l < kMaxCodeLen && w12 >= bi->code_end[l]) ++l;
+  const uint32_t idx = bi->first_idx[l] + ((w12 - bi->code_end[l - 1]) >> (kMaxCodeLen - l));
+  return (uint32_t)bi->syms[idx & 255u] | ((uint32_t)l << 24) | (1u << 30);
 }
 
 __device__ __forceinline__ uint4 ld_chunk(uintptr_t addr, uintptr_t lo_lim) {
@@ -616,7 +625,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   for (int lb = 0; lb < bpc; ++lb) {
     const DecBlockInfo* bi = &infos[lb];
     if (b0 + lb < n_blocks && bi->ok && bi->raw_size != 0) {
-      build_dtable<kDecBits, 3>(bi, comp + offsets[b0 + lb] + bi->syms_off, tables + (size_t)lb * kDecEntries,
+      build_dtable<kDecBits, 3>(bi, bi->syms, tables + (size_t)lb * kDecEntries,
                                 region + (size_t)lb * kDecEntries, tid, nthreads);
     }
   }
@@ -635,6 +644,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uintptr_t e16 = 16, lo_lim = 0;
   uint32_t acc = 0;            // bits 0..5: bits consumed from the window, bits 6..: symbols in the row
   uint32_t rd = 0, staged = 0, cidx = 0;
+  uint32_t ob = 0;             // pending output symbols (fewer than 4), first symbol in the low byte
   bool bad_lane = false;
   if (active) {
     const uint8_t* blk = comp + offsets[b];
@@ -665,7 +675,8 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // shared-space addresses, kept in registers
   const uint32_t t_addr = smem_u32(tables + (size_t)(lb < bpc ? lb : 0) * kDecEntries);
   const uint32_t col = smem_u32(region) + (uint32_t)warp * (16 * 32 * 4) + 4u * (uint32_t)lane;  // word i at col + (i & 15) * 128
-  const uint32_t row = smem_u32(region) + (uint32_t)nwarps * (16 * 32 * 4) + (uint32_t)tid * kDecRow;
+  // output staging: word j (4 symbols) of this lane at row + j * 128 -- lane-private bank, conflict-free
+  const uint32_t row = smem_u32(region) + (uint32_t)nwarps * (16 * 32 * 4) + (uint32_t)warp * (32 * kDecRow) + 4u * (uint32_t)lane;
   // make the three addresses opaque so that they stay in registers instead of being recomputed
   // from tid / %ctaid inside the lookup loop
   asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
@@ -708,16 +719,22 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     const uint32_t target = left < 16 ? left : 16;
     const uint32_t limit = target << 6;
     uint32_t rdo = (rd & 15) * 128;
+    uint32_t wofs = 0;  // byte offset of the next row word
     while (acc < limit) {
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
       uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
-      const uint32_t wr = row + (acc >> 6);
-      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6.. (the only loop-carried chain)
-      // a 12-bit code: the entry holds both siblings, the next bit picks one (off the critical chain)
-      if ((e & (15u << 24)) == (12u << 24) && (win & (1u << (31 - kDecBits)))) e >>= 8;
-      sts_u8(wr, e);
-      sts_u8(wr + 1, e >> 8);
-      sts_u8(wr + 2, e >> 16);
+      if (e < (1u << 30)) e = escape_decode(bi, win);  // rare: code longer than kDecBits
+      // append the entry's symbols (unused bytes are zero) to the pending output word
+      const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (symbols pending in ob)
+      const uint32_t v = e & 0xffffffu;
+      const uint32_t old = acc;
+      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6.. (the loop-carried chain)
+      ob |= v << sh;
+      if ((acc ^ old) & 0x100u) {  // the symbol count crossed a multiple of 4: one row word is complete
+        sts_u32(row + wofs, ob);
+        wofs += 128;
+        ob = shr_c(v, 32u - sh);
+      }
       if (acc & 32u) {
         hi = lo;
         lo = nx;
@@ -731,22 +748,18 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       if (target == 16 && (((uintptr_t)outp) & 15) == 0) {
         uint4 v;
         v.x = lds_u32(row + 0);
-        v.y = lds_u32(row + 4);
-        v.z = lds_u32(row + 8);
-        v.w = lds_u32(row + 12);
+        v.y = lds_u32(row + 128);
+        v.z = lds_u32(row + 256);
+        v.w = lds_u32(row + 384);
         *reinterpret_cast<uint4*>(outp) = v;
       } else {
-        for (uint32_t i = 0; i < target; ++i) outp[i] = (uint8_t)lds_u8(row + i);
+        sts_u32(row + wofs, ob);  // partial word
+        for (uint32_t i = 0; i < target; ++i) outp[i] = (uint8_t)lds_u8(row + (i >> 2) * 128 + (i & 3));
       }
       outp += target;
       left -= target;
-      // symbols decoded beyond this round's 16 (at most 2) open the next round
-      const uint32_t extra = (acc >> 6) - target;
-      if (extra) {
-        sts_u8(row + 0, lds_u8(row + target));
-        sts_u8(row + 1, lds_u8(row + target + 1));
-      }
-      acc = (acc & 63u) | (extra << 6);
+      // symbols decoded beyond this round (at most 2) stay in ob and open the next round
+      acc -= target << 6;
     }
   }
 }
