@@ -34,7 +34,9 @@ def build(force=False, verbose=False):
     """Compile csrc/*.cu into libhufb200.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    # HUF_DEFS="-DHUF_DEC_BITS=10 ..." lets a tuning sweep rebuild variants (never set in production)
+    extra = os.environ.get("HUF_DEFS", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

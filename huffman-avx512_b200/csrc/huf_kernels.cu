@@ -470,10 +470,12 @@ struct DecBlockInfo {
 // (generalises Decoder2x, codec/huffman.cpp:642-704).
 //   entry: byte0..2 = symbols, bits 24..27 = stream bits consumed, bits 30..31 = symbol count.
 //   BITS = 12, MAXSYM = 2: exactly the reference's two-symbol table (pair iff l1+l2 <= 12, :653).
-//   BITS = kDecBits (11), MAXSYM = 3: what the decode kernel uses: three symbols per lookup cut
-//     the lookups (the kernel is bound by shared-memory wavefronts), 8 KiB instead of 16 KiB per
-//     block keeps enough warps resident; a prefix that belongs to a code longer than BITS gets
-//     symbol count 0 and is resolved arithmetically from the canonical code ranges (escape_decode).
+//   BITS = 11, MAXSYM = 3: what the decode kernel uses: three symbols per lookup cut the
+//     lookups, 8 KiB instead of 16 KiB per block keeps more stream groups resident.  A 12-bit
+//     code cannot be resolved by 11 bits, but 12-bit codes come in sibling pairs that share
+//     their first 11 bits (the code is complete), so such an entry holds both candidates
+//     (byte0 for next bit 0, byte1 for next bit 1), one symbol, 12 bits consumed -- and
+//     "12 bits consumed" is the marker, since every other entry of this table consumes <= 11.
 // L1 (u8 per entry: the first code's own length, 15 = none) is scratch that may be reused
 // afterwards; the first symbol sits in byte 0 of T from the first pass on and never changes.
 template <int BITS, int MAXSYM>
@@ -492,7 +494,12 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
       L1[e] = (uint8_t)l;
     } else {
       L1[e] = 15;  // never fits behind another symbol
-      T[e] = 0;    // symbol count 0: code longer than BITS (or a malformed table) -> escape
+      uint32_t ent = (12u << 24) | (1u << 30);  // sibling pair of 12-bit codes (or a malformed table)
+      if (BITS == kMaxCodeLen - 1 && v < bi->code_end[kMaxCodeLen]) {
+        const uint32_t idx = bi->first_idx[kMaxCodeLen] + (v - bi->code_end[kMaxCodeLen - 1]);
+        ent |= (idx < bi->num_syms ? syms[idx] : 0u) | ((idx + 1 < bi->num_syms ? syms[idx + 1] : 0u) << 8);
+      }
+      T[e] = ent;
     }
   }
   __syncthreads();
@@ -514,10 +521,7 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
   __syncthreads();
 }
 
-#ifndef HUF_DEC_BITS
-#define HUF_DEC_BITS 11
-#endif
-constexpr int kDecBits = HUF_DEC_BITS;
+constexpr int kDecBits = 11;  // the sibling-pair entries need exactly one unresolved bit
 constexpr int kDecEntries = 1 << kDecBits;
 constexpr int kDecRow = 20;  // bytes of output staging per lane: 16 per round + 2 spill-over
 
@@ -557,17 +561,6 @@ __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int 
   if (bi->payload_off > comp_size) return;
   for (uint32_t i = 0; i < nsyms; ++i) bi->syms[i] = blk[pos + i];
   bi->ok = 1;
-}
-
-// One symbol whose code is longer than the table index: canonical codes of length l occupy
-// [code_end[l-1], code_end[l]) of the left-aligned 12-bit code space in sorted_syms order
-// (ForallCodes, codec/huffman.cpp:260-284).  Returns a table-format entry.
-__device__ __forceinline__ uint32_t escape_decode(const DecBlockInfo* bi, uint32_t win) {
-  const uint32_t w12 = win >> 20;
-  int l = kDecBits + 1;
-  while (l < kMaxCodeLen && w12 >= bi->code_end[l]) ++l;
-  const uint32_t idx = bi->first_idx[l] + ((w12 - bi->code_end[l - 1]) >> (kMaxCodeLen - l));
-  return (uint32_t)bi->syms[idx & 255u] | ((uint32_t)l << 24) | (1u << 30);
 }
 
 __device__ __forceinline__ uint4 ld_chunk(uintptr_t addr, uintptr_t lo_lim) {
@@ -699,8 +692,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   }
   uint32_t hi = lds_u32(col + (rd & 15) * 128);
   uint32_t lo = lds_u32(col + ((rd + 1) & 15) * 128);
-  uint32_t nx = lds_u32(col + ((rd + 2) & 15) * 128);
-  rd += 3;
+  rd += 2;
 
   const uint32_t max_left = __reduce_max_sync(0xffffffffu, left);
   for (uint32_t round = 0; round * 16 < max_left; ++round) {
@@ -722,13 +714,15 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     uint32_t wofs = 0;  // byte offset of the next row word
     while (acc < limit) {
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
-      uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
-      if (e < (1u << 30)) e = escape_decode(bi, win);  // rare: code longer than kDecBits
-      // append the entry's symbols (unused bytes are zero) to the pending output word
+      const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
+      const uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
       const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (symbols pending in ob)
-      const uint32_t v = e & 0xffffffu;
       const uint32_t old = acc;
-      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6.. (the loop-carried chain)
+      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
+      // everything below hangs off that chain
+      uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
+      if ((e & (15u << 24)) == (12u << 24))  // a 12-bit code: the next bit picks one of the two siblings
+        v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
       ob |= v << sh;
       if ((acc ^ old) & 0x100u) {  // the symbol count crossed a multiple of 4: one row word is complete
         sts_u32(row + wofs, ob);
@@ -737,8 +731,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       }
       if (acc & 32u) {
         hi = lo;
-        lo = nx;
-        nx = lds_u32(col + rdo);
+        lo = nxw;
         rdo = (rdo + 128) & (15 * 128);
         ++rd;
         acc -= 32;
