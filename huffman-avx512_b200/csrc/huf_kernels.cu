@@ -129,11 +129,16 @@ __global__ void __launch_bounds__(32) k_make_table(const uint32_t* __restrict__ 
 // Fused compress kernel: one CTA per block (CompressMulti<K>, codec/huffman.cpp:738-846)
 // ===========================================================================
 constexpr int kRingWords = 256;  // per-warp staging ring, in 32-bit stream words (1 KiB, 1 KiB-aligned)
+// Staged mode (slices of at most kStageSlice symbols): a warp keeps the whole bitstream of its
+// stream in shared memory, so the stream's size is known without a separate length pass.
+constexpr int kStageSlice = 4096;
+constexpr int kStageWords = 1280;  // 5 KiB per warp = 10 bits/symbol; longer streams take the ring path
 
 struct CompSmem {
   union {
     uint32_t bins[256 * 32];                  // histogram phase
-    uint32_t ring[kCompWarps][kRingWords];    // encode phase
+    uint32_t ring[kCompWarps][kRingWords];    // encode phase, ring mode
+    uint32_t stage[kCompWarps][kStageWords];  // encode phase, staged mode (each 1 KiB-aligned)
   } u;
   uint32_t hist[256];
   HufTable tab;
@@ -141,6 +146,7 @@ struct CompSmem {
   unsigned long long stream_bits[kMaxK];
   uint32_t region_end[kMaxK];  // cumulative end offsets relative to the payload start (:772-786)
   uint32_t bad;
+  uint32_t run_end;            // staged mode: end offset of the last placed region
 };
 
 __device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) {  // shift >= 32 gives 0
@@ -225,6 +231,15 @@ __device__ __forceinline__ void ring_put(uint32_t ring_base, uint32_t pos, uint3
   const uint32_t a1 = ring_base | ((a0 + 4u) & 0x3fcu);
   red_or_shared(a0, t >> o);
   red_or_shared(a1, shl_c(t, 32u - o));
+}
+
+// Same into a linear (non-wrapping) staging buffer.
+__device__ __forceinline__ void stage_put(uint32_t stage_base, uint32_t pos, uint32_t code, uint32_t len) {
+  const uint32_t t = shl_c(code, 32u - len);
+  const uint32_t o = pos & 31u;
+  const uint32_t a0 = stage_base + ((pos >> 3) & ~3u);
+  red_or_shared(a0, t >> o);
+  red_or_shared(a0 + 4u, shl_c(t, 32u - o));
 }
 
 // Four table entries (first symbol first) -> the two pair codes and lengths.  c01 may carry
@@ -333,12 +348,99 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_bas
   __syncwarp();
 }
 
+// Staged mode, step 1: encode the whole stream into the warp's linear staging buffer (zeroed by
+// the previous copy-out).  Returns the stream's bit total; *overflow is set when it does not fit
+// (then only the count is valid and the caller falls back to the ring path).
+__device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* enc, uint32_t stage_base,
+                                                               const uint8_t* sp, uint32_t sz, bool* overflow) {
+  const int lane = lane_id();
+  const bool aligned = (((uintptr_t)sp) & 15) == 0;
+  unsigned long long bitpos = 0;
+  bool over = false;
+  for (uint32_t base = 0; base < sz; base += 512) {
+    const uint32_t off = base + lane * 16;
+    const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
+    const uint4 v = load16(sp, off, valid, aligned);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t c01[4], l01[4], c23[4], l23[4];
+    if (valid == 16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        quad_code(enc[byte_of(w[j], 0)], enc[byte_of(w[j], 1)], enc[byte_of(w[j], 2)], enc[byte_of(w[j], 3)],
+                  c01[j], l01[j], c23[j], l23[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t e[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = (uint32_t)(4 * j + i) < valid ? enc[byte_of(w[j], i)] : 0u;
+        quad_code(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
+      }
+    }
+    uint32_t lq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lq[j] = l01[j] + l23[j];
+    const uint32_t lane_len = (lq[0] + lq[1]) + (lq[2] + lq[3]);
+    const uint32_t incl = warp_incl_scan(lane_len);
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    // a symbol without a code makes `total` huge and lands here as an overflow, too
+    if (bitpos + total > (unsigned long long)(kStageWords - 1) * 32) over = true;
+    if (!over) {
+      uint32_t pos = (uint32_t)bitpos + (incl - lane_len);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (lq[j] <= 32) {
+          stage_put(stage_base, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
+        } else {
+          stage_put(stage_base, pos, c01[j], l01[j]);
+          stage_put(stage_base, pos + l01[j], c23[j], l23[j]);
+        }
+        pos += lq[j];
+      }
+    }
+    bitpos += total;
+  }
+  __syncwarp();
+  *overflow = over;
+  return bitpos;
+}
+
+// Staged mode, step 2: the staged stream words go out as aligned 128-byte rows below e_off
+// (same alignment algebra as encode_stream_warp); the buffer is left zeroed.
+__device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long long bits, uint8_t* dst,
+                                            uint32_t e_off, uint32_t region) {
+  const int lane = lane_id();
+  const uint32_t r = ((e_off - 1u) & 3u) + 1u;
+  const uint32_t sh = 8u * r;
+  const uint32_t e_al = e_off - r;
+  const uint32_t s_al = (e_off - region + 3u) & ~3u;
+  const uint32_t m_last = (e_al - s_al) >> 2;  // inclusive
+  uint32_t* out_lane = reinterpret_cast<uint32_t*>(dst + e_al) - lane;
+  const uint32_t wtot = (uint32_t)((bits + 31) >> 5);
+  uint32_t carry = 0;
+  for (uint32_t m0 = 0; m0 <= m_last; m0 += 32) {
+    const uint32_t m = m0 + lane;
+    uint32_t lo = 0;
+    if (m < wtot) {
+      lo = lds_u32(stage_base + 4u * m);
+      sts_u32(stage_base + 4u * m, 0);
+    }
+    uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
+    if (lane == 0) hi = carry;
+    carry = __shfl_sync(0xffffffffu, lo, 31);
+    if (m <= m_last) *(out_lane - m0) = __funnelshift_lc(lo, hi, sh);
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kCompThreads, kCompCtasPerSm)
 k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_size, int K,
                   uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
                   uint32_t* __restrict__ comp_sizes, const HufTable* __restrict__ shared_tab,
                   int check_presence, uint32_t* __restrict__ status) {
-  __shared__ __align__(1024) CompSmem sm;
+  extern __shared__ __align__(1024) uint8_t comp_smem[];  // dynamic: the layout exceeds the 48 KiB static limit
+  CompSmem& sm = *reinterpret_cast<CompSmem*>(comp_smem);
+  if (smem_u32(comp_smem) & 1023u) __trap();  // ring_put/stage buffers rely on 1 KiB alignment
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -370,9 +472,12 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist, &sm.tab, &sm.sc);
       else build_table_warp<uint32_t, unsigned long long>(sm.hist, &sm.tab, &sm.sc);
     }
+    // slices short enough for the staged mode?  (uniform over the grid: depends on the geometry only)
+    const bool staged = (block_size + (uint32_t)K - 1) / (uint32_t)K <= (uint32_t)kStageSlice;
     {
-      uint32_t* rz = &sm.u.ring[0][0];
-      for (int i = tid; i < kCompWarps * kRingWords; i += kCompThreads) rz[i] = 0;
+      uint4* rz = reinterpret_cast<uint4*>(&sm.u.stage[0][0]);
+      const int nz = (staged ? kCompWarps * kStageWords : kCompWarps * kRingWords) / 4;
+      for (int i = tid; i < nz; i += kCompThreads) rz[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     if (shared_tab != nullptr && check_presence && tid < 256) {
@@ -398,6 +503,72 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       } else v = sm.tab.sorted_syms[i - 8 - npop];
       dst[i] = v;
     }
+    const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
+    if (staged) {
+      // ---- staged mode: rounds of kCompWarps streams; encode into shared memory, then place
+      if (tid == 0) {
+        sm.run_end = 0;
+        for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;  // slop bytes sharing a word with the header
+      }
+      __syncthreads();
+      bool bad = sm.bad != 0;  // presence check of the shared-table mode
+      for (int s0 = 0; s0 < K && !bad; s0 += kCompWarps) {
+        const int s = s0 + warp;
+        uint32_t st = 0, sz = 0;
+        bool over = false;
+        unsigned long long bits = 0;
+        const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
+        if (s < K) {
+          slice_geom(bn, K, s, st, sz);
+          bits = encode_stream_staged_warp(sm.tab.enc, stage_base, src + st, sz, &over);
+          if (bits > 12ull * sz) atomicOr(&sm.bad, 1u);  // a symbol without a code
+          if (lane == 0) sm.stream_bits[s] = bits;
+        }
+        __syncthreads();
+        if (tid == 0) {  // region ends of this round (:772-786)
+          uint32_t pos = sm.run_end;
+          for (int t = s0; t < K && t < s0 + kCompWarps; ++t) {
+            pos += (uint32_t)((sm.stream_bits[t] + 7) >> 3) + kSlop;
+            sm.region_end[t] = pos;
+          }
+          sm.run_end = pos;
+        }
+        __syncthreads();
+        bad = sm.bad != 0;
+        if (s < K && !bad) {
+          const uint32_t e_off = hdr_total + sm.region_end[s];
+          const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
+          if (!over) {
+            copy_stream_out_warp(stage_base, bits, dst, e_off, region);
+          } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
+            for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
+            __syncwarp();
+            encode_stream_warp(sm.tab.enc, stage_base, src + st, sz, bits, dst, e_off, region);
+          }
+        }
+      }
+      __syncthreads();
+      bad = sm.bad != 0;
+      if (bad) {
+        if (tid == 0) {
+          comp_sizes[b] = 0;
+          if (status) atomicOr(status, 1u);
+        }
+      } else {
+        for (int s = tid; s < K - 1; s += kCompThreads) {  // end_offset table (:809-811)
+          const uint32_t e = sm.region_end[s];
+          uint8_t* p = dst + hdr + 4 * s;
+          p[0] = (uint8_t)e;
+          p[1] = (uint8_t)(e >> 8);
+          p[2] = (uint8_t)(e >> 16);
+          p[3] = (uint8_t)(e >> 24);
+        }
+        if (tid == 0) comp_sizes[b] = hdr_total + sm.region_end[K - 1];
+      }
+      __syncthreads();
+      continue;
+    }
+    // ---- ring mode (long slices): per-stream bit totals first (:772-782)
     for (int s = warp; s < K; s += kCompWarps) {
       uint32_t st, sz;
       slice_geom(bn, K, s, st, sz);
@@ -415,7 +586,6 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       }
     }
     __syncthreads();
-    const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
     if (bad) {
       if (tid == 0) {
         comp_sizes[b] = 0;
@@ -879,7 +1049,14 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
                             uint8_t* d_out, uint64_t slot_stride, uint32_t* d_sizes, const void* d_table,
                             int check_presence, uint32_t* d_status, int grid, cudaStream_t st) {
   if (n_blocks == 0) return cudaSuccess;
-  k_compress_blocks<<<grid, kCompThreads, 0, st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride,
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(CompSmem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k_compress_blocks<<<grid, kCompThreads, sizeof(CompSmem), st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride,
                                                    d_sizes, reinterpret_cast<const HufTable*>(d_table),
                                                    check_presence, d_status);
   return cudaGetLastError();

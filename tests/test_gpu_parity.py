@@ -166,3 +166,29 @@ def test_block_container_roundtrip(huf, oracle):
                 assert blk == oracle.compress(k, raw_blk), (k, bs, b)
         assert pos == len(cont)
     assert huf.decompress_blocks(huf.compress_blocks(32, 131072, b"")) == b""
+
+
+def test_staged_encoder_overflow_fallback(huf, oracle):
+    """One slice made only of rare symbols (12-bit codes, > 10 bits/symbol) overflows the per-warp
+    staging buffer of the staged encoder and must take the ring path; bytes still equal the oracle."""
+    rng = np.random.default_rng(99)
+    k, bs = 32, 131072
+    sl = bs // k
+    blk = np.full(bs, ord("a"), dtype=np.uint8)
+    blk[::7] = ord("b")
+    blk[::11] = ord("c")
+    for s in (5, 17, 31):  # three slices of rare symbols
+        blk[s * sl:(s + 1) * sl] = rng.integers(40, 256, sl, dtype=np.uint8)
+    data = blk.tobytes() * 2 + bytes(rng.integers(0, 256, 1000, dtype=np.uint8))
+    want0 = oracle.compress(k, data[:bs])
+    sizes = np.frombuffer(want0[8 + 13:], dtype=np.uint8)  # not used, just make sure it parses
+    assert huf.compress(k, data[:bs]) == want0
+    cont = huf.compress_blocks(k, bs, data)
+    assert huf.decompress_blocks(cont) == data
+    nb = 3
+    idx = np.frombuffer(cont[32:32 + 4 * nb], dtype="<u4")
+    assert cont[32 + 4 * nb: 32 + 4 * nb + int(idx[0])] == want0
+    # the rare slices really are longer than 10 bits/symbol
+    cd = oracle.make_coding(oracle.histogram(data[:bs]))
+    bits = int(cd["code_len"][blk[5 * sl:6 * sl]].sum())
+    assert bits > 10 * sl
