@@ -75,6 +75,42 @@ struct Workspace {
 };
 thread_local Workspace g_ws;
 
+// Two-deep copy/compute pipeline for the host-pointer container calls: chunk c+1's host->device
+// copy and kernels overlap chunk c's device->host copy (PCIe is full duplex; the kernels are
+// ~20x faster than either copy).
+struct Pipe {
+  cudaStream_t st = nullptr;
+  int dev = -1;
+  DevBuf in, out, sizes, offsets, packed, misc;
+  // pinned landing zone for the per-chunk results (a pageable destination would make the
+  // device->host copy synchronous and stall the pipeline): [0] chunk bytes (u64), [1] status
+  unsigned long long* meta = nullptr;
+  cudaError_t ready() {
+    int cur = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return e;
+    if (st && dev != cur) {
+      cudaStreamDestroy(st);
+      st = nullptr;
+    }
+    if (!st) {
+      e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return e;
+      dev = cur;
+    }
+    if (!meta) {
+      e = cudaHostAlloc(reinterpret_cast<void**>(&meta), 64, cudaHostAllocDefault);
+      if (e != cudaSuccess) {
+        meta = nullptr;
+        return e;
+      }
+    }
+    return cudaSuccess;
+  }
+};
+thread_local Pipe g_pipe[2];
+constexpr size_t kChunkBytes = (size_t)32 << 20;  // raw bytes per pipeline chunk
+
 struct DevInfo {
   int dev = -1;
   int sms = 0;
@@ -391,35 +427,88 @@ int hufb200_compress_blocks(int k, size_t block_size, const uint8_t* raw, size_t
   if (!out_len || (!raw && n) || (!out && cap)) return fail(HUFB200_E_INVALID, "null pointer");
   const size_t nb = hufb200_blocks_count(n, block_size);
   if (nb >> 31) return fail(HUFB200_E_INVALID, "too many blocks");
-  std::vector<uint32_t> sizes;
-  size_t stride = 0;
-  int rc = compress_host(k, block_size, raw, n, (uint32_t)nb, nullptr, 0, &sizes, &stride);
-  if (rc) return rc;
-  size_t total = kContainerHeader + 4 * nb;
-  for (size_t b = 0; b < nb; ++b) total += sizes[b];
-  *out_len = total;
-  if (total > cap) return fail(HUFB200_E_NOSPACE, "need %zu bytes, have %zu", total, cap);
-  // header: magic, version|k, block_size, raw_size(u64), n_blocks, reserved
-  memset(out, 0, kContainerHeader);
-  const uint32_t magic = kMagic, vk = 1u | ((uint32_t)k << 16), bs = (uint32_t)block_size, nb32 = (uint32_t)nb;
-  const uint64_t rs = n;
-  memcpy(out + 0, &magic, 4);
-  memcpy(out + 4, &vk, 4);
-  memcpy(out + 8, &bs, 4);
-  memcpy(out + 12, &nb32, 4);
-  memcpy(out + 16, &rs, 8);
-  if (nb) memcpy(out + kContainerHeader, sizes.data(), 4 * nb);
-  // pack on the device, one D2H copy of the payload
-  Workspace& ws = g_ws;
-  const size_t payload = total - kContainerHeader - 4 * nb;
-  if (nb) {
-    CU(ws.offsets.reserve(sizeof(uint64_t) * (nb + 1)));
-    CU(ws.in.reserve(payload + 16));  // the raw input is no longer needed
-    CU(launch_pack(ws.out.as<uint8_t>(), stride, ws.sizes.as<uint32_t>(), (uint32_t)nb, ws.in.as<uint8_t>(),
-                   ws.offsets.as<unsigned long long>(), ws.offsets.as<unsigned long long>() + nb, 0));
-    g_launches.fetch_add(2, std::memory_order_relaxed);
-    CU(cudaMemcpy(out + kContainerHeader + 4 * nb, ws.in.p, payload, cudaMemcpyDeviceToHost));
+  const size_t index_end = kContainerHeader + 4 * nb;
+  if (index_end <= cap) {
+    // header: magic, version|k, block_size, n_blocks, raw_size(u64), reserved
+    memset(out, 0, kContainerHeader);
+    const uint32_t magic = kMagic, vk = 1u | ((uint32_t)k << 16), bs = (uint32_t)block_size, nb32 = (uint32_t)nb;
+    const uint64_t rs = n;
+    memcpy(out + 0, &magic, 4);
+    memcpy(out + 4, &vk, 4);
+    memcpy(out + 8, &bs, 4);
+    memcpy(out + 12, &nb32, 4);
+    memcpy(out + 16, &rs, 8);
   }
+  const size_t stride = hufb200_slot_stride(block_size, k);
+  size_t per = kChunkBytes / block_size;  // blocks per chunk
+  if (per < 1) per = 1;
+  const size_t n_chunks = (nb + per - 1) / per;
+  size_t total = index_end;  // running container size
+  bool fits = index_end <= cap;
+  struct Pending {
+    bool live = false;
+    size_t blk0 = 0, nblk = 0;
+  } pend[2];
+  // second half of a chunk: its sizes and total are on the host -> payload device->host
+  auto finish = [&](int slot) -> int {
+    Pending& pd = pend[slot];
+    if (!pd.live) return HUFB200_OK;
+    Pipe& pp = g_pipe[slot];
+    CU(cudaStreamSynchronize(pp.st));
+    pd.live = false;
+    const unsigned long long chunk_total = pp.meta[0];
+    if (pp.meta[1]) return fail(HUFB200_E_CORRUPT, "kernel reported a malformed block");
+    if (fits && total + chunk_total <= cap) {
+      CU(cudaMemcpyAsync(out + total, pp.packed.p, chunk_total, cudaMemcpyDeviceToHost, pp.st));
+    } else {
+      fits = false;
+    }
+    total += chunk_total;
+    return HUFB200_OK;
+  };
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const int slot = (int)(c & 1);
+    Pipe& pp = g_pipe[slot];
+    int rc = finish(slot);  // the chunk that used this slot two iterations ago
+    if (rc) return rc;
+    CU(pp.ready());
+    CU(cudaStreamSynchronize(pp.st));  // its payload copy must be done before the buffers are reused
+    const size_t blk0 = c * per, nblk = (nb - blk0 < per) ? nb - blk0 : per;
+    const size_t off = blk0 * block_size, len = (n - off < nblk * block_size) ? n - off : nblk * block_size;
+    CU(pp.in.reserve(len + 16));
+    CU(pp.out.reserve(stride * nblk));
+    CU(pp.sizes.reserve(4 * (nblk + 1)));
+    CU(pp.offsets.reserve(8 * (nblk + 2)));
+    CU(pp.packed.reserve(hufb200_compress_bound(block_size, k) * nblk + 32));
+    CU(pp.misc.reserve(256));
+    CU(cudaMemcpyAsync(pp.in.p, raw + off, len, cudaMemcpyHostToDevice, pp.st));
+    CU(cudaMemsetAsync(pp.misc.p, 0, 4, pp.st));
+    rc = do_compress_dev(k, block_size, pp.in.as<uint8_t>(), len, (uint32_t)nblk, pp.out.as<uint8_t>(), stride,
+                         pp.sizes.as<uint32_t>(), nullptr, 0, pp.misc.as<uint32_t>(), pp.st);
+    if (rc) return rc;
+    unsigned long long* d_off = pp.offsets.as<unsigned long long>();
+    CU(launch_pack(pp.out.as<uint8_t>(), stride, pp.sizes.as<uint32_t>(), (uint32_t)nblk, pp.packed.as<uint8_t>(),
+                   d_off, d_off + nblk, pp.st));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    Pending& pd = pend[slot];
+    pd.live = true;
+    pd.blk0 = blk0;
+    pd.nblk = nblk;
+    if (index_end <= cap) {
+      CU(cudaMemcpyAsync(out + kContainerHeader + 4 * blk0, pp.sizes.p, 4 * nblk, cudaMemcpyDeviceToHost, pp.st));
+    }
+    pp.meta[1] = 0;
+    CU(cudaMemcpyAsync(&pp.meta[0], d_off + nblk, 8, cudaMemcpyDeviceToHost, pp.st));
+    CU(cudaMemcpyAsync(&pp.meta[1], pp.misc.p, 4, cudaMemcpyDeviceToHost, pp.st));
+  }
+  for (size_t c = n_chunks; c < n_chunks + 2; ++c) {  // drain in issue order
+    int rc = finish((int)(c & 1));
+    if (rc) return rc;
+  }
+  for (int slot = 0; slot < 2; ++slot)
+    if (g_pipe[slot].st) CU(cudaStreamSynchronize(g_pipe[slot].st));
+  *out_len = total;
+  if (!fits) return fail(HUFB200_E_NOSPACE, "need %zu bytes, have %zu", total, cap);
   return HUFB200_OK;
 }
 
@@ -464,26 +553,49 @@ int hufb200_decompress_blocks(const uint8_t* c, size_t n, uint8_t* out, size_t c
     sum += s;
   }
   if (sum != payload_n) return fail(HUFB200_E_CORRUPT, "block sizes do not add up to the payload size");
-  Workspace& ws = g_ws;
-  CU(ws.in.reserve(payload_n + 32));
-  CU(ws.out.reserve(rs + 16));
-  CU(ws.sizes.reserve(4 * (nb + 1)));
-  CU(ws.offsets.reserve(8 * (nb + 1)));
-  CU(ws.misc.reserve(256));
-  CU(cudaMemcpyAsync(ws.in.p, payload, payload_n, cudaMemcpyHostToDevice, 0));
-  CU(cudaMemcpyAsync(ws.sizes.p, index, 4 * nb, cudaMemcpyHostToDevice, 0));
-  CU(cudaMemsetAsync(ws.misc.p, 0, 4, 0));
-  CU(launch_scan_sizes(ws.sizes.as<uint32_t>(), (uint32_t)nb, ws.offsets.as<unsigned long long>(), nullptr, 0));
-  rc = hufb200_decompress_blocks_dev(k, bs, ws.in.as<uint8_t>(), ws.offsets.as<uint64_t>(),
-                                     ws.sizes.as<uint32_t>(), nb, ws.out.as<uint8_t>(), rs,
-                                     ws.misc.as<uint32_t>(), nullptr);
-  if (rc) return rc;
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  uint32_t status = 0;
-  CU(cudaMemcpyAsync(&status, ws.misc.p, 4, cudaMemcpyDeviceToHost, 0));
-  CU(cudaMemcpyAsync(out, ws.out.p, rs, cudaMemcpyDeviceToHost, 0));
-  CU(cudaStreamSynchronize(0));
-  if (status) return fail(HUFB200_E_CORRUPT, "malformed block in container");
+  // chunked two-stream pipeline: payload host->device, decode, raw device->host
+  size_t per = kChunkBytes / bs;
+  if (per < 1) per = 1;
+  const size_t n_chunks = (nb + per - 1) / per;
+  bool used[2] = {false, false};
+  size_t pay_off = 0;
+  for (size_t ci = 0; ci < n_chunks; ++ci) {
+    const int slot = (int)(ci & 1);
+    Pipe& pp = g_pipe[slot];
+    CU(pp.ready());
+    CU(cudaStreamSynchronize(pp.st));  // buffers of chunk ci-2 are free again
+    if (used[slot] && pp.meta[1]) return fail(HUFB200_E_CORRUPT, "malformed block in container");
+    const size_t blk0 = ci * per, nblk = (nb - blk0 < per) ? nb - blk0 : per;
+    const size_t roff = blk0 * bs, rlen = (rs - roff < nblk * bs) ? rs - roff : nblk * bs;
+    size_t clen = 0;
+    for (size_t j = 0; j < nblk; ++j) {
+      uint32_t sz;
+      memcpy(&sz, index + 4 * (blk0 + j), 4);
+      clen += sz;
+    }
+    CU(pp.in.reserve(clen + 32));
+    CU(pp.out.reserve(rlen + 16));
+    CU(pp.sizes.reserve(4 * (nblk + 1)));
+    CU(pp.offsets.reserve(8 * (nblk + 1)));
+    CU(pp.misc.reserve(256));
+    CU(cudaMemcpyAsync(pp.in.p, payload + pay_off, clen, cudaMemcpyHostToDevice, pp.st));
+    CU(cudaMemcpyAsync(pp.sizes.p, index + 4 * blk0, 4 * nblk, cudaMemcpyHostToDevice, pp.st));
+    CU(launch_scan_sizes(pp.sizes.as<uint32_t>(), (uint32_t)nblk, pp.offsets.as<unsigned long long>(), nullptr, pp.st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CU(cudaMemsetAsync(pp.misc.p, 0, 4, pp.st));
+    rc = hufb200_decompress_blocks_dev(k, bs, pp.in.as<uint8_t>(), pp.offsets.as<uint64_t>(), pp.sizes.as<uint32_t>(),
+                                       nblk, pp.out.as<uint8_t>(), rlen, pp.misc.as<uint32_t>(), pp.st);
+    if (rc) return rc;
+    pp.meta[1] = 0;
+    CU(cudaMemcpyAsync(&pp.meta[1], pp.misc.p, 4, cudaMemcpyDeviceToHost, pp.st));
+    CU(cudaMemcpyAsync(out + roff, pp.out.p, rlen, cudaMemcpyDeviceToHost, pp.st));
+    used[slot] = true;
+    pay_off += clen;
+  }
+  for (int slot = 0; slot < 2; ++slot)
+    if (used[slot]) CU(cudaStreamSynchronize(g_pipe[slot].st));
+  for (int slot = 0; slot < 2; ++slot)
+    if (used[slot] && g_pipe[slot].meta[1]) return fail(HUFB200_E_CORRUPT, "malformed block in container");
   return HUFB200_OK;
 }
 
