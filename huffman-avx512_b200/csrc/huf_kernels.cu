@@ -175,13 +175,40 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
 
 // Loads the 16 symbols [off, off+16) of a slice as four little-endian words; symbols
-// beyond `valid` read as 0 and are masked by the caller.
-__device__ __forceinline__ uint4 load16(const uint8_t* sp, uint32_t off, uint32_t valid, bool aligned) {
-  if (aligned && valid >= 16) return *reinterpret_cast<const uint4*>(sp + off);
+// beyond `valid` read as 0 and are masked by the caller.  Slices that do not start on a
+// 16-byte boundary (K does not divide the block nicely, e.g. K = 48) take two aligned 128-bit
+// loads and a byte funnel shift; the misalignment is the same for every lane and iteration of
+// a stream, so the switch is warp-uniform.  `lim` = end of the input buffer (no reads past it).
+__device__ __forceinline__ uint4 load16(const uint8_t* sp, uint32_t off, uint32_t valid, bool aligned,
+                                        const uint8_t* lim) {
+  const uint8_t* a = sp + off;
+  if (valid >= 16) {
+    if (aligned) return *reinterpret_cast<const uint4*>(a);
+    const uintptr_t base = (uintptr_t)a & ~(uintptr_t)15;
+    if (base + 32 <= (uintptr_t)lim) {
+      const uint4 A = *reinterpret_cast<const uint4*>(base);
+      const uint4 B = *reinterpret_cast<const uint4*>(base + 16);
+      const uint32_t sh = 8u * (uint32_t)((uintptr_t)a & 3);
+      switch (((uintptr_t)a >> 2) & 3) {
+        case 0:
+          return make_uint4(__funnelshift_r(A.x, A.y, sh), __funnelshift_r(A.y, A.z, sh),
+                            __funnelshift_r(A.z, A.w, sh), __funnelshift_r(A.w, B.x, sh));
+        case 1:
+          return make_uint4(__funnelshift_r(A.y, A.z, sh), __funnelshift_r(A.z, A.w, sh),
+                            __funnelshift_r(A.w, B.x, sh), __funnelshift_r(B.x, B.y, sh));
+        case 2:
+          return make_uint4(__funnelshift_r(A.z, A.w, sh), __funnelshift_r(A.w, B.x, sh),
+                            __funnelshift_r(B.x, B.y, sh), __funnelshift_r(B.y, B.z, sh));
+        default:
+          return make_uint4(__funnelshift_r(A.w, B.x, sh), __funnelshift_r(B.x, B.y, sh),
+                            __funnelshift_r(B.y, B.z, sh), __funnelshift_r(B.z, B.w, sh));
+      }
+    }
+  }
   uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < 16; ++i)
-    if ((uint32_t)i < valid) w[i >> 2] |= (uint32_t)sp[off + i] << (8 * (i & 3));
+    if ((uint32_t)i < valid) w[i >> 2] |= (uint32_t)a[i] << (8 * (i & 3));
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -193,14 +220,14 @@ __device__ __forceinline__ uint32_t word_entries(const uint32_t* enc, uint32_t w
 
 // Per-stream bit total (the reference derives it from per-stream histograms, :776-782).
 __device__ inline unsigned long long stream_length_warp(const uint32_t* enc, const uint8_t* sp,
-                                                        uint32_t sz, uint32_t* bad) {
+                                                        uint32_t sz, uint32_t* bad, const uint8_t* lim) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
   unsigned long long acc = 0;
   uint32_t flag = 0;
   const uint32_t full = sz & ~511u;
   for (uint32_t base = 0; base < full; base += 512) {
-    const uint4 v = load16(sp, base + lane * 16, 16, aligned);
+    const uint4 v = load16(sp, base + lane * 16, 16, aligned, lim);
     // 16 entries: lengths <= 16*12 in bits 16..23, kEncInvalid entries pile up in bits 30+
     const uint32_t s = ((word_entries(enc, v.x) >> 16) + (word_entries(enc, v.y) >> 16)) +
                        ((word_entries(enc, v.z) >> 16) + (word_entries(enc, v.w) >> 16));
@@ -263,7 +290,7 @@ __device__ __forceinline__ void quad_code(uint32_t e0, uint32_t e1, uint32_t e2,
 // emits aligned 128-byte rows; complete stream words leave the ring 32 at a time.
 __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_base, const uint8_t* sp,
                                           uint32_t sz, unsigned long long bits, uint8_t* dst,
-                                          uint32_t e_off, uint32_t region) {
+                                          uint32_t e_off, uint32_t region, const uint8_t* lim) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
   const uint32_t r = ((e_off - 1u) & 3u) + 1u;
@@ -280,7 +307,7 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_bas
   for (uint32_t base = 0; base < sz; base += 512) {
     const uint32_t off = base + lane * 16;
     const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
-    const uint4 v = load16(sp, off, valid, aligned);
+    const uint4 v = load16(sp, off, valid, aligned, lim);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t c01[4], l01[4], c23[4], l23[4];
     if (valid == 16) {
@@ -352,7 +379,8 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_bas
 // the previous copy-out).  Returns the stream's bit total; *overflow is set when it does not fit
 // (then only the count is valid and the caller falls back to the ring path).
 __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* enc, uint32_t stage_base,
-                                                               const uint8_t* sp, uint32_t sz, bool* overflow) {
+                                                               const uint8_t* sp, uint32_t sz, bool* overflow,
+                                                               const uint8_t* lim) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
   unsigned long long bitpos = 0;
@@ -360,7 +388,7 @@ __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* e
   for (uint32_t base = 0; base < sz; base += 512) {
     const uint32_t off = base + lane * 16;
     const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
-    const uint4 v = load16(sp, off, valid, aligned);
+    const uint4 v = load16(sp, off, valid, aligned, lim);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t c01[4], l01[4], c23[4], l23[4];
     if (valid == 16) {
@@ -520,7 +548,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
         const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
         if (s < K) {
           slice_geom(bn, K, s, st, sz);
-          bits = encode_stream_staged_warp(sm.tab.enc, stage_base, src + st, sz, &over);
+          bits = encode_stream_staged_warp(sm.tab.enc, stage_base, src + st, sz, &over, raw + n);
           if (bits > 12ull * sz) atomicOr(&sm.bad, 1u);  // a symbol without a code
           if (lane == 0) sm.stream_bits[s] = bits;
         }
@@ -543,7 +571,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
           } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
             for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
             __syncwarp();
-            encode_stream_warp(sm.tab.enc, stage_base, src + st, sz, bits, dst, e_off, region);
+            encode_stream_warp(sm.tab.enc, stage_base, src + st, sz, bits, dst, e_off, region, raw + n);
           }
         }
       }
@@ -572,7 +600,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
     for (int s = warp; s < K; s += kCompWarps) {
       uint32_t st, sz;
       slice_geom(bn, K, s, st, sz);
-      const unsigned long long bits = stream_length_warp(sm.tab.enc, src + st, sz, &sm.bad);
+      const unsigned long long bits = stream_length_warp(sm.tab.enc, src + st, sz, &sm.bad, raw + n);
       if (lane == 0) sm.stream_bits[s] = bits;
     }
     __syncthreads();
@@ -613,7 +641,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       slice_geom(bn, K, s, st, sz);
       const uint32_t e_off = hdr_total + sm.region_end[s];
       const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
-      encode_stream_warp(sm.tab.enc, smem_u32(&sm.u.ring[warp][0]), src + st, sz, sm.stream_bits[s], dst, e_off, region);
+      encode_stream_warp(sm.tab.enc, smem_u32(&sm.u.ring[warp][0]), src + st, sz, sm.stream_bits[s], dst, e_off, region, raw + n);
     }
     __syncthreads();
   }
@@ -864,8 +892,10 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t lo = lds_u32(col + ((rd + 1) & 15) * 128);
   rd += 2;
 
-  const uint32_t max_left = __reduce_max_sync(0xffffffffu, left);
-  for (uint32_t round = 0; round * 16 < max_left; ++round) {
+  // The first round of a lane whose slice does not start on a 16-byte boundary is a short one
+  // that brings it there, so that every later full round is one aligned 128-bit store.
+  uint32_t head = (uint32_t)((16 - ((uintptr_t)outp & 15)) & 15);
+  while (__any_sync(0xffffffffu, left != 0)) {
     // Top up the ring: a round consumes at most 7 words.  The chunk stored now was requested
     // at the previous top-up, so its latency is hidden unless the stream runs at > 8 bits/symbol.
     while (staged - rd < 11) {
@@ -878,7 +908,9 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
       ++cidx;
     }
-    const uint32_t target = left < 16 ? left : 16;
+    uint32_t target = head ? head : 16u;
+    head = 0;
+    if (target > left) target = left;
     const uint32_t limit = target << 6;
     uint32_t rdo = (rd & 15) * 128;
     uint32_t wofs = 0;  // byte offset of the next row word
@@ -918,6 +950,14 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       } else {
         sts_u32(row + wofs, ob);  // partial word
         for (uint32_t i = 0; i < target; ++i) outp[i] = (uint8_t)lds_u8(row + (i >> 2) * 128 + (i & 3));
+        if (target != 16) {  // short round: re-base the (at most 2) symbols decoded beyond it into ob
+          const uint32_t extra = (acc >> 6) - target;
+          ob = 0;
+          for (uint32_t i = 0; i < extra; ++i) {
+            const uint32_t j = target + i;
+            ob |= lds_u8(row + (j >> 2) * 128 + (j & 3)) << (8 * i);
+          }
+        }
       }
       outp += target;
       left -= target;
