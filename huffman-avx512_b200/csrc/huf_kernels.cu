@@ -41,15 +41,16 @@ __device__ __forceinline__ uint32_t bins_reduce(const uint32_t* bins, int t) {
 }
 
 // Accumulates the bytes [p, p+n) into the CTA's lane-private bins (all threads).
-__device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p, uint64_t n) {
+// (t, nt): index of the calling thread among the nt threads that take part (whole warps).
+__device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p, uint64_t n, uint32_t t, uint32_t nt) {
   uint32_t* bl = bins + lane_id();
   const uint64_t mis = (16 - ((uintptr_t)p & 15)) & 15;
   const uint64_t head = mis < n ? mis : n;
-  for (uint64_t i = threadIdx.x; i < head; i += blockDim.x) atomicAdd(bl + ((uint32_t)p[i] << 5), 1u);
+  for (uint64_t i = t; i < head; i += nt) atomicAdd(bl + ((uint32_t)p[i] << 5), 1u);
   const uint4* v = reinterpret_cast<const uint4*>(p + head);
   const uint64_t nvec = (n - head) >> 4;
-  uint64_t i = threadIdx.x;
-  const uint64_t step = blockDim.x;
+  uint64_t i = t;
+  const uint64_t step = nt;
   for (; i + 3 * step < nvec; i += 4 * step) {  // 4 loads in flight per thread
     const uint4 a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
     bins_add_vec(bl, a);
@@ -59,7 +60,7 @@ __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p
   }
   for (; i < nvec; i += step) bins_add_vec(bl, v[i]);
   const uint64_t done = head + (nvec << 4);
-  for (uint64_t j = done + threadIdx.x; j < n; j += blockDim.x) atomicAdd(bl + ((uint32_t)p[j] << 5), 1u);
+  for (uint64_t j = done + t; j < n; j += nt) atomicAdd(bl + ((uint32_t)p[j] << 5), 1u);
 }
 
 __global__ void __launch_bounds__(kHistThreads)
@@ -75,7 +76,7 @@ k_histogram(const uint8_t* __restrict__ in, uint64_t n, unsigned long long* __re
     uint64_t len = per * 16;
     if (beg + len > n) len = n - beg;
     // 32-bit lane counters: a CTA's share is processed in pieces of < 2^32 bytes
-    bins_accumulate(bins, in + beg, len);
+    bins_accumulate(bins, in + beg, len, threadIdx.x, blockDim.x);
   }
   __syncthreads();
   if (threadIdx.x < 256) {
@@ -140,7 +141,7 @@ struct CompSmem {
     uint32_t ring[kCompWarps][kRingWords];    // encode phase, ring mode
     uint32_t stage[kCompWarps][kStageWords];  // encode phase, staged mode (each 1 KiB-aligned)
   } u;
-  uint32_t hist[256];
+  uint32_t hist[2][256];  // [cur] block being encoded, [cur^1] next block (counted during the table build)
   HufTable tab;
   TableScratch sc;
   unsigned long long stream_bits[kMaxK];
@@ -473,33 +474,59 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
+  // Software pipeline over the blocks of this CTA: while warp 0 builds block b's table (serial,
+  // ~6k instructions), the other warps already count the histogram of the CTA's next block.
+  const bool need_hist = (shared_tab == nullptr) || check_presence;
+  int cur = 0;
+  auto block_len = [&](uint32_t blk) -> uint32_t {
+    const uint64_t o = (uint64_t)blk * block_size;
+    return (uint32_t)((n - o) < (uint64_t)block_size ? (n - o) : (uint64_t)block_size);
+  };
+  auto zero_bins = [&]() {
+    uint4* z = reinterpret_cast<uint4*>(sm.u.bins);
+    for (int i = tid; i < 256 * 32 / 4; i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
+  };
+  if (need_hist && blockIdx.x < n_blocks) {  // prologue: histogram of the first block, all warps
+    zero_bins();
+    __syncthreads();
+    bins_accumulate(sm.u.bins, raw + (uint64_t)blockIdx.x * block_size, block_len(blockIdx.x), tid, kCompThreads);
+    __syncthreads();
+    if (tid < 256) sm.hist[0][tid] = bins_reduce(sm.u.bins, tid);
+    __syncthreads();
+  }
   for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
     const uint64_t boff = (uint64_t)b * block_size;
     const uint8_t* src = raw + boff;
-    const uint32_t bn = (uint32_t)((n - boff) < (uint64_t)block_size ? (n - boff) : (uint64_t)block_size);
+    const uint32_t bn = block_len(b);
     uint8_t* dst = out + (uint64_t)b * slot_stride;
+    const uint32_t nb_next = b + gridDim.x;
+    const bool have_next = need_hist && nb_next < n_blocks;
     if (tid == 0) sm.bad = 0;
 
-    // ---- phase 1: histogram (skipped in shared-table mode unless presence is checked)
-    const bool need_hist = (shared_tab == nullptr) || check_presence;
-    if (need_hist) {
-      uint4* z = reinterpret_cast<uint4*>(sm.u.bins);
-      for (int i = tid; i < 256 * 32 / 4; i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
-      __syncthreads();
-      bins_accumulate(sm.u.bins, src, bn);
-      __syncthreads();
-      if (tid < 256) sm.hist[tid] = bins_reduce(sm.u.bins, tid);
-      __syncthreads();
-    }
-    // ---- phase 2: table (warp 0) while the other warps clear the staging rings
+    // ---- phase 1+2: table of block b (warp 0) || histogram of the next block (other warps)
+    if (have_next) zero_bins();  // the staging buffers of the previous block are dead by now
+    __syncthreads();
     if (shared_tab != nullptr) {
       const uint32_t* s = reinterpret_cast<const uint32_t*>(shared_tab);
       uint32_t* d = reinterpret_cast<uint32_t*>(&sm.tab);
       for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += kCompThreads) d[i] = s[i];
-    } else if (warp == 0) {
-      if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist, &sm.tab, &sm.sc);
-      else build_table_warp<uint32_t, unsigned long long>(sm.hist, &sm.tab, &sm.sc);
     }
+    if (warp == 0) {
+      if (shared_tab == nullptr) {
+        if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist[cur], &sm.tab, &sm.sc);
+        else build_table_warp<uint32_t, unsigned long long>(sm.hist[cur], &sm.tab, &sm.sc);
+      }
+    } else if (have_next) {
+      bins_accumulate(sm.u.bins, raw + (uint64_t)nb_next * block_size, block_len(nb_next), tid - 32,
+                      kCompThreads - 32);
+    }
+    __syncthreads();
+    if (have_next && tid < 256) sm.hist[cur ^ 1][tid] = bins_reduce(sm.u.bins, tid);
+    if (shared_tab != nullptr && check_presence && tid < 256) {
+      if (sm.hist[cur][tid] != 0 && sm.tab.enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
+    }
+    cur ^= 1;  // sm.hist[cur] now belongs to the next block
+    __syncthreads();
     // slices short enough for the staged mode?  (uniform over the grid: depends on the geometry only)
     const bool staged = (block_size + (uint32_t)K - 1) / (uint32_t)K <= (uint32_t)kStageSlice;
     {
@@ -508,9 +535,6 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       for (int i = tid; i < nz; i += kCompThreads) rz[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    if (shared_tab != nullptr && check_presence && tid < 256) {
-      if (sm.hist[tid] != 0 && sm.tab.enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
-    }
 
     // ---- phase 3: header prefix (:799-808) and per-stream bit totals (:772-782)
     const uint32_t hdr = sm.tab.hdr_len;
