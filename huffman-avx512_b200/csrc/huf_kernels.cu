@@ -147,7 +147,6 @@ struct CompSmem {
   unsigned long long stream_bits[kMaxK];
   uint32_t region_end[kMaxK];  // cumulative end offsets relative to the payload start (:772-786)
   uint32_t bad;
-  uint32_t run_end;            // staged mode: end offset of the last placed region
 };
 
 __device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) {  // shift >= 32 gives 0
@@ -386,10 +385,16 @@ __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* e
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
   unsigned long long bitpos = 0;
   bool over = false;
+  // the next iteration's 16 symbols are requested one iteration ahead
+  uint32_t noff = lane * 16;
+  uint32_t nvalid = noff < sz ? (sz - noff < 16 ? sz - noff : 16) : 0;
+  uint4 vnext = load16(sp, noff, nvalid, aligned, lim);
   for (uint32_t base = 0; base < sz; base += 512) {
-    const uint32_t off = base + lane * 16;
-    const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
-    const uint4 v = load16(sp, off, valid, aligned, lim);
+    const uint4 v = vnext;
+    const uint32_t valid = nvalid;
+    noff += 512;
+    nvalid = noff < sz ? (sz - noff < 16 ? sz - noff : 16) : 0;
+    if (base + 512 < sz) vnext = load16(sp, noff, nvalid, aligned, lim);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t c01[4], l01[4], c23[4], l23[4];
     if (valid == 16) {
@@ -558,13 +563,13 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
     const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
     if (staged) {
       // ---- staged mode: rounds of kCompWarps streams; encode into shared memory, then place
-      if (tid == 0) {
-        sm.run_end = 0;
+      if (tid == 0)
         for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;  // slop bytes sharing a word with the header
-      }
-      __syncthreads();
-      bool bad = sm.bad != 0;  // presence check of the shared-table mode
-      for (int s0 = 0; s0 < K && !bad; s0 += kCompWarps) {
+      // One barrier per round: after it every warp derives the round's region ends itself from
+      // the published bit totals (:772-786).  The loop always runs all rounds (a block flagged
+      // bad only skips its global writes), so the barriers stay uniform.
+      uint32_t run_end = 0;  // end offset of the last placed region, identical in all threads
+      for (int s0 = 0; s0 < K; s0 += kCompWarps) {
         const int s = s0 + warp;
         uint32_t st = 0, sz = 0;
         bool over = false;
@@ -577,30 +582,34 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
           if (lane == 0) sm.stream_bits[s] = bits;
         }
         __syncthreads();
-        if (tid == 0) {  // region ends of this round (:772-786)
-          uint32_t pos = sm.run_end;
-          for (int t = s0; t < K && t < s0 + kCompWarps; ++t) {
-            pos += (uint32_t)((sm.stream_bits[t] + 7) >> 3) + kSlop;
-            sm.region_end[t] = pos;
+        const bool bad_now = sm.bad != 0;  // covers every stream up to this round
+        uint32_t my_end = 0, my_region = 0;
+        for (int t = s0; t < K && t < s0 + kCompWarps; ++t) {
+          const uint32_t reg = (uint32_t)((sm.stream_bits[t] + 7) >> 3) + kSlop;
+          run_end += reg;
+          if (t == s) {
+            my_end = run_end;
+            my_region = reg;
           }
-          sm.run_end = pos;
         }
-        __syncthreads();
-        bad = sm.bad != 0;
-        if (s < K && !bad) {
-          const uint32_t e_off = hdr_total + sm.region_end[s];
-          const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
-          if (!over) {
-            copy_stream_out_warp(stage_base, bits, dst, e_off, region);
-          } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
+        if (s < K) {
+          if (lane == 0) sm.region_end[s] = my_end;
+          if (!bad_now) {
+            const uint32_t e_off = hdr_total + my_end;
+            if (!over) {
+              copy_stream_out_warp(stage_base, bits, dst, e_off, my_region);
+            } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
+              for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
+              __syncwarp();
+              encode_stream_warp(sm.tab.enc, stage_base, src + st, sz, bits, dst, e_off, my_region, raw + n);
+            }
+          } else {  // leave the staging buffer clean for the next block
             for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
-            __syncwarp();
-            encode_stream_warp(sm.tab.enc, stage_base, src + st, sz, bits, dst, e_off, region, raw + n);
           }
         }
       }
       __syncthreads();
-      bad = sm.bad != 0;
+      bool bad = sm.bad != 0;
       if (bad) {
         if (tid == 0) {
           comp_sizes[b] = 0;
