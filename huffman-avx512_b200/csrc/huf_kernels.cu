@@ -881,9 +881,10 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       const uint8_t* p = blk + bi->ends_off + 4 * s;
       e_off = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
     }
-    if (e_off > payload) {
+    if (e_off > payload) {  // corrupt end offset: produce nothing and read nothing through it
       bad_lane = true;
       sz = 0;
+      e_off = 0;
     }
     left = sz;
     outp = raw + (uint64_t)b * block_size + st;

@@ -192,3 +192,43 @@ def test_staged_encoder_overflow_fallback(huf, oracle):
     cd = oracle.make_coding(oracle.histogram(data[:bs]))
     bits = int(cd["code_len"][blk[5 * sl:6 * sl]].sum())
     assert bits > 10 * sl
+
+
+def test_decoder_survives_corrupt_input(huf):
+    """Hardened decoder: corrupted buffers give an error code or bounded
+    garbage -- never a fault, a hang or an out-of-bounds write -- and the device stays usable."""
+    rng = np.random.default_rng(2024)
+    good_data = biased(200_000, seed=5)
+    for k in (4, 32, 48):
+        good = bytearray(huf.compress(k, good_data))
+        for trial in range(40):
+            bad = bytearray(good)
+            kind = trial % 4
+            if kind == 0:    # flip bytes in the header / table / end offsets
+                for _ in range(3):
+                    bad[int(rng.integers(0, 8 + 13 + 60 + 4 * k))] ^= int(rng.integers(1, 256))
+            elif kind == 1:  # flip payload bytes
+                for _ in range(20):
+                    bad[int(rng.integers(0, len(bad)))] ^= int(rng.integers(1, 256))
+            elif kind == 2:  # truncate
+                bad = bad[: int(rng.integers(1, len(bad)))]
+            else:            # end offsets beyond the payload
+                pos = 8 + 13 + 40
+                bad[pos: pos + 4] = (0xfffffff0).to_bytes(4, "little")
+            try:
+                out = huf.decompress(k, bytes(bad))
+                assert len(out) == int.from_bytes(bytes(bad[:4]), "little")
+            except huf.HufError as e:
+                assert e.code in (-1, -2, -4)
+        assert huf.decompress(k, bytes(good)) == good_data
+    # same through the block container
+    cont = bytearray(huf.compress_blocks(32, 65536, good_data))
+    for trial in range(20):
+        bad = bytearray(cont)
+        for _ in range(10):
+            bad[int(rng.integers(32, len(bad)))] ^= int(rng.integers(1, 256))
+        try:
+            huf.decompress_blocks(bytes(bad))
+        except huf.HufError as e:
+            assert e.code in (-1, -2, -4)
+    assert huf.decompress_blocks(bytes(cont)) == good_data
