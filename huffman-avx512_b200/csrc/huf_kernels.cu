@@ -141,8 +141,8 @@ struct CompSmem {
     uint32_t ring[kCompWarps][kRingWords];    // encode phase, ring mode
     uint32_t stage[kCompWarps][kStageWords];  // encode phase, staged mode (each 1 KiB-aligned)
   } u;
-  uint32_t hist[2][256];  // [cur] block being encoded, [cur^1] next block (counted during the table build)
-  HufTable tab;
+  uint32_t hist[2][256];  // [cur] block being encoded, [cur^1] the CTA's next block
+  HufTable tab[2];        // same double buffering: the builder warp fills [cur^1] during the encode of [cur]
   TableScratch sc;
   unsigned long long stream_bits[kMaxK];
   uint32_t region_end[kMaxK];  // cumulative end offsets relative to the payload start (:772-786)
@@ -467,6 +467,145 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
   __syncwarp();
 }
 
+// Worker-only barrier (named barrier 1): the table-builder warp never takes part in it.
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory"); }
+
+// Everything the workers do for one block once its table is in `tab`: header, streams, sizes.
+__device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, const uint8_t* raw, uint64_t n,
+                                            const uint8_t* src, uint32_t bn, uint32_t block_size, int K,
+                                            uint8_t* dst, uint32_t* comp_size_out, uint32_t* status) {
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  // slices short enough for the staged mode?  (uniform over the grid: depends on the geometry only)
+  const bool staged = (block_size + (uint32_t)K - 1) / (uint32_t)K <= (uint32_t)kStageSlice;
+  {
+    uint4* rz = reinterpret_cast<uint4*>(&sm.u.stage[0][0]);
+    const int nz = (staged ? kCompWarps * kStageWords : kCompWarps * kRingWords) / 4;
+    for (int i = tid; i < nz; i += kWorkThreads) rz[i] = make_uint4(0, 0, 0, 0);
+  }
+  // ---- header prefix (:799-808)
+  const uint32_t hdr = tab.hdr_len;
+  const uint32_t mask = tab.len_mask;
+  const uint32_t npop = (uint32_t)__popc(mask);
+  for (uint32_t i = tid; i < hdr; i += kWorkThreads) {
+    uint8_t v;
+    if (i < 4) v = (uint8_t)(bn >> (8 * i));
+    else if (i < 8) v = (uint8_t)(mask >> (8 * (i - 4)));
+    else if (i < 8 + npop) {
+      int bit = 0;  // position of the (i-8)-th set bit of the mask
+      for (uint32_t seen = 0;; ++bit)
+        if ((mask >> bit) & 1u) {
+          if (seen == i - 8) break;
+          ++seen;
+        }
+      v = (uint8_t)tab.len_count[bit];  // 256 wraps to 0 (:804)
+    } else v = tab.sorted_syms[i - 8 - npop];
+    dst[i] = v;
+  }
+  const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
+  if (tid == 0)
+    for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;  // slop bytes sharing a word with the header
+  worker_sync();  // staging zeroed
+
+  if (staged) {
+    // ---- staged mode: rounds of kCompWarps streams; encode into shared memory, then place.
+    // One barrier per round: after it every warp derives the round's region ends itself from
+    // the published bit totals (:772-786).  The loop always runs all rounds (a block flagged
+    // bad only skips its global writes), so the barriers stay uniform.
+    uint32_t run_end = 0;  // end offset of the last placed region, identical in all threads
+    for (int s0 = 0; s0 < K; s0 += kCompWarps) {
+      const int s = s0 + warp;
+      uint32_t st = 0, sz = 0;
+      bool over = false;
+      unsigned long long bits = 0;
+      const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
+      if (s < K) {
+        slice_geom(bn, K, s, st, sz);
+        bits = encode_stream_staged_warp(tab.enc, stage_base, src + st, sz, &over, raw + n);
+        if (bits > 12ull * sz) atomicOr(&sm.bad, 1u);  // a symbol without a code
+        if (lane == 0) sm.stream_bits[s] = bits;
+      }
+      worker_sync();
+      const bool bad_now = sm.bad != 0;  // covers every stream up to this round
+      uint32_t my_end = 0, my_region = 0;
+      for (int t = s0; t < K && t < s0 + kCompWarps; ++t) {
+        const uint32_t reg = (uint32_t)((sm.stream_bits[t] + 7) >> 3) + kSlop;
+        run_end += reg;
+        if (t == s) {
+          my_end = run_end;
+          my_region = reg;
+        }
+      }
+      if (s < K) {
+        if (lane == 0) sm.region_end[s] = my_end;
+        if (!bad_now) {
+          const uint32_t e_off = hdr_total + my_end;
+          if (!over) {
+            copy_stream_out_warp(stage_base, bits, dst, e_off, my_region);
+          } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
+            for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
+            __syncwarp();
+            encode_stream_warp(tab.enc, stage_base, src + st, sz, bits, dst, e_off, my_region, raw + n);
+          }
+        } else {  // leave the staging buffer clean for the next block
+          for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
+        }
+      }
+    }
+    worker_sync();
+  } else {
+    // ---- ring mode (long slices): per-stream bit totals first (:772-782)
+    for (int s = warp; s < K; s += kCompWarps) {
+      uint32_t st, sz;
+      slice_geom(bn, K, s, st, sz);
+      const unsigned long long bits = stream_length_warp(tab.enc, src + st, sz, &sm.bad, raw + n);
+      if (lane == 0) sm.stream_bits[s] = bits;
+    }
+    worker_sync();
+    if (tid == 0) {  // region offsets (:783-786)
+      uint32_t pos = 0;
+      for (int s = 0; s < K; ++s) {
+        pos += (uint32_t)((sm.stream_bits[s] + 7) >> 3) + kSlop;
+        sm.region_end[s] = pos;
+      }
+    }
+    worker_sync();
+    if (sm.bad == 0) {  // encode, one warp per stream
+      for (int s = warp; s < K; s += kCompWarps) {
+        uint32_t st, sz;
+        slice_geom(bn, K, s, st, sz);
+        const uint32_t e_off = hdr_total + sm.region_end[s];
+        const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
+        encode_stream_warp(tab.enc, smem_u32(&sm.u.ring[warp][0]), src + st, sz, sm.stream_bits[s], dst, e_off,
+                           region, raw + n);
+      }
+    }
+    worker_sync();
+  }
+  // ---- end_offset table (:809-811) and the block's size
+  if (sm.bad != 0) {
+    if (tid == 0) {
+      *comp_size_out = 0;
+      if (status) atomicOr(status, 1u);
+    }
+  } else {
+    for (int s = tid; s < K - 1; s += kWorkThreads) {
+      const uint32_t e = sm.region_end[s];
+      uint8_t* p = dst + hdr + 4 * s;
+      p[0] = (uint8_t)e;
+      p[1] = (uint8_t)(e >> 8);
+      p[2] = (uint8_t)(e >> 16);
+      p[3] = (uint8_t)(e >> 24);
+    }
+    if (tid == 0) *comp_size_out = hdr_total + sm.region_end[K - 1];
+  }
+}
+
+// Warp-specialised CTA: warps 0..7 are workers (histogram, encode), warp 8 builds tables.  While
+// the workers encode block b with table[cur], the builder turns the histogram of the CTA's next
+// block (counted by the workers just before) into table[cur^1]; its ~6k serial instructions
+// disappear behind the encode.
 __global__ void __launch_bounds__(kCompThreads, kCompCtasPerSm)
 k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_size, int K,
                   uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
@@ -476,207 +615,66 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
   CompSmem& sm = *reinterpret_cast<CompSmem*>(comp_smem);
   if (smem_u32(comp_smem) & 1023u) __trap();  // ring_put/stage buffers rely on 1 KiB alignment
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
+  const bool builder = tid >= kWorkThreads;  // the last warp
+  const bool own_tables = shared_tab == nullptr;
+  const bool need_hist = own_tables || check_presence;
 
-  // Software pipeline over the blocks of this CTA: while warp 0 builds block b's table (serial,
-  // ~6k instructions), the other warps already count the histogram of the CTA's next block.
-  const bool need_hist = (shared_tab == nullptr) || check_presence;
-  int cur = 0;
   auto block_len = [&](uint32_t blk) -> uint32_t {
     const uint64_t o = (uint64_t)blk * block_size;
     return (uint32_t)((n - o) < (uint64_t)block_size ? (n - o) : (uint64_t)block_size);
   };
-  auto zero_bins = [&]() {
+  // workers: histogram of block `blk` into sm.hist[slot]
+  auto histogram_block = [&](uint32_t blk, int slot) {
     uint4* z = reinterpret_cast<uint4*>(sm.u.bins);
-    for (int i = tid; i < 256 * 32 / 4; i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 256 * 32 / 4; i += kWorkThreads) z[i] = make_uint4(0, 0, 0, 0);
+    worker_sync();
+    bins_accumulate(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
+    worker_sync();
+    sm.hist[slot][tid] = bins_reduce(sm.u.bins, tid);  // kWorkThreads == 256 bins
   };
-  if (need_hist && blockIdx.x < n_blocks) {  // prologue: histogram of the first block, all warps
-    zero_bins();
-    __syncthreads();
-    bins_accumulate(sm.u.bins, raw + (uint64_t)blockIdx.x * block_size, block_len(blockIdx.x), tid, kCompThreads);
-    __syncthreads();
-    if (tid < 256) sm.hist[0][tid] = bins_reduce(sm.u.bins, tid);
-    __syncthreads();
-  }
-  for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-    const uint64_t boff = (uint64_t)b * block_size;
-    const uint8_t* src = raw + boff;
-    const uint32_t bn = block_len(b);
-    uint8_t* dst = out + (uint64_t)b * slot_stride;
-    const uint32_t nb_next = b + gridDim.x;
-    const bool have_next = need_hist && nb_next < n_blocks;
-    if (tid == 0) sm.bad = 0;
+  auto build_table = [&](int slot) {
+    if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist[slot], &sm.tab[slot], &sm.sc);
+    else build_table_warp<uint32_t, unsigned long long>(sm.hist[slot], &sm.tab[slot], &sm.sc);
+  };
 
-    // ---- phase 1+2: table of block b (warp 0) || histogram of the next block (other warps)
-    if (have_next) zero_bins();  // the staging buffers of the previous block are dead by now
-    __syncthreads();
-    if (shared_tab != nullptr) {
-      const uint32_t* s = reinterpret_cast<const uint32_t*>(shared_tab);
-      uint32_t* d = reinterpret_cast<uint32_t*>(&sm.tab);
+  if (blockIdx.x >= n_blocks) return;
+  // ---- prologue: first block's histogram and table (or the shared table into both slots)
+  if (!builder && need_hist) histogram_block(blockIdx.x, 0);
+  if (!own_tables) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(shared_tab);
+    for (int t = 0; t < 2; ++t) {
+      uint32_t* d = reinterpret_cast<uint32_t*>(&sm.tab[t]);
       for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += kCompThreads) d[i] = s[i];
     }
-    if (warp == 0) {
-      if (shared_tab == nullptr) {
-        if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist[cur], &sm.tab, &sm.sc);
-        else build_table_warp<uint32_t, unsigned long long>(sm.hist[cur], &sm.tab, &sm.sc);
-      }
-    } else if (have_next) {
-      bins_accumulate(sm.u.bins, raw + (uint64_t)nb_next * block_size, block_len(nb_next), tid - 32,
-                      kCompThreads - 32);
-    }
-    __syncthreads();
-    if (have_next && tid < 256) sm.hist[cur ^ 1][tid] = bins_reduce(sm.u.bins, tid);
-    if (shared_tab != nullptr && check_presence && tid < 256) {
-      if (sm.hist[cur][tid] != 0 && sm.tab.enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
-    }
-    cur ^= 1;  // sm.hist[cur] now belongs to the next block
-    __syncthreads();
-    // slices short enough for the staged mode?  (uniform over the grid: depends on the geometry only)
-    const bool staged = (block_size + (uint32_t)K - 1) / (uint32_t)K <= (uint32_t)kStageSlice;
-    {
-      uint4* rz = reinterpret_cast<uint4*>(&sm.u.stage[0][0]);
-      const int nz = (staged ? kCompWarps * kStageWords : kCompWarps * kRingWords) / 4;
-      for (int i = tid; i < nz; i += kCompThreads) rz[i] = make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
+  }
+  __syncthreads();
+  if (builder && own_tables) build_table(0);
+  __syncthreads();
 
-    // ---- phase 3: header prefix (:799-808) and per-stream bit totals (:772-782)
-    const uint32_t hdr = sm.tab.hdr_len;
-    const uint32_t mask = sm.tab.len_mask;
-    const uint32_t npop = (uint32_t)__popc(mask);
-    for (uint32_t i = tid; i < hdr; i += kCompThreads) {
-      uint8_t v;
-      if (i < 4) v = (uint8_t)(bn >> (8 * i));
-      else if (i < 8) v = (uint8_t)(mask >> (8 * (i - 4)));
-      else if (i < 8 + npop) {
-        int bit = 0;  // position of the (i-8)-th set bit of the mask
-        for (uint32_t seen = 0;; ++bit)
-          if ((mask >> bit) & 1u) {
-            if (seen == i - 8) break;
-            ++seen;
-          }
-        v = (uint8_t)sm.tab.len_count[bit];                // 256 wraps to 0 (:804)
-      } else v = sm.tab.sorted_syms[i - 8 - npop];
-      dst[i] = v;
-    }
-    const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
-    if (staged) {
-      // ---- staged mode: rounds of kCompWarps streams; encode into shared memory, then place
-      if (tid == 0)
-        for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;  // slop bytes sharing a word with the header
-      // One barrier per round: after it every warp derives the round's region ends itself from
-      // the published bit totals (:772-786).  The loop always runs all rounds (a block flagged
-      // bad only skips its global writes), so the barriers stay uniform.
-      uint32_t run_end = 0;  // end offset of the last placed region, identical in all threads
-      for (int s0 = 0; s0 < K; s0 += kCompWarps) {
-        const int s = s0 + warp;
-        uint32_t st = 0, sz = 0;
-        bool over = false;
-        unsigned long long bits = 0;
-        const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
-        if (s < K) {
-          slice_geom(bn, K, s, st, sz);
-          bits = encode_stream_staged_warp(sm.tab.enc, stage_base, src + st, sz, &over, raw + n);
-          if (bits > 12ull * sz) atomicOr(&sm.bad, 1u);  // a symbol without a code
-          if (lane == 0) sm.stream_bits[s] = bits;
-        }
-        __syncthreads();
-        const bool bad_now = sm.bad != 0;  // covers every stream up to this round
-        uint32_t my_end = 0, my_region = 0;
-        for (int t = s0; t < K && t < s0 + kCompWarps; ++t) {
-          const uint32_t reg = (uint32_t)((sm.stream_bits[t] + 7) >> 3) + kSlop;
-          run_end += reg;
-          if (t == s) {
-            my_end = run_end;
-            my_region = reg;
-          }
-        }
-        if (s < K) {
-          if (lane == 0) sm.region_end[s] = my_end;
-          if (!bad_now) {
-            const uint32_t e_off = hdr_total + my_end;
-            if (!over) {
-              copy_stream_out_warp(stage_base, bits, dst, e_off, my_region);
-            } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
-              for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
-              __syncwarp();
-              encode_stream_warp(sm.tab.enc, stage_base, src + st, sz, bits, dst, e_off, my_region, raw + n);
-            }
-          } else {  // leave the staging buffer clean for the next block
-            for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
-          }
-        }
-      }
-      __syncthreads();
-      bool bad = sm.bad != 0;
-      if (bad) {
-        if (tid == 0) {
-          comp_sizes[b] = 0;
-          if (status) atomicOr(status, 1u);
-        }
-      } else {
-        for (int s = tid; s < K - 1; s += kCompThreads) {  // end_offset table (:809-811)
-          const uint32_t e = sm.region_end[s];
-          uint8_t* p = dst + hdr + 4 * s;
-          p[0] = (uint8_t)e;
-          p[1] = (uint8_t)(e >> 8);
-          p[2] = (uint8_t)(e >> 16);
-          p[3] = (uint8_t)(e >> 24);
-        }
-        if (tid == 0) comp_sizes[b] = hdr_total + sm.region_end[K - 1];
-      }
-      __syncthreads();
-      continue;
-    }
-    // ---- ring mode (long slices): per-stream bit totals first (:772-782)
-    for (int s = warp; s < K; s += kCompWarps) {
-      uint32_t st, sz;
-      slice_geom(bn, K, s, st, sz);
-      const unsigned long long bits = stream_length_warp(sm.tab.enc, src + st, sz, &sm.bad, raw + n);
-      if (lane == 0) sm.stream_bits[s] = bits;
+  int cur = 0;
+  for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+    const uint32_t nb_next = b + gridDim.x;
+    const bool have_next = need_hist && nb_next < n_blocks;
+    // ---- phase A: the workers count the next block (the staging buffers of the previous block
+    //      are dead, the bins alias them); the builder has nothing to do yet
+    if (!builder) {
+      if (tid == 0) sm.bad = 0;
+      if (have_next) histogram_block(nb_next, cur ^ 1);
     }
     __syncthreads();
-    const bool bad = sm.bad != 0;
-    // ---- phase 4: region offsets and the end_offset table (:783-786, :809-811)
-    if (tid == 0) {
-      uint32_t pos = 0;
-      for (int s = 0; s < K; ++s) {
-        pos += (uint32_t)((sm.stream_bits[s] + 7) >> 3) + kSlop;
-        sm.region_end[s] = pos;
+    // ---- phase B: workers encode block b with table[cur] || builder makes table[cur^1]
+    if (builder) {
+      if (have_next && own_tables) build_table(cur ^ 1);
+    } else {
+      if (!own_tables && check_presence) {  // every symbol of the block needs a code in the supplied table
+        if (sm.hist[cur][tid] != 0 && sm.tab[cur].enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
       }
+      const uint64_t boff = (uint64_t)b * block_size;
+      encode_block_workers(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
+                           out + (uint64_t)b * slot_stride, comp_sizes + b, status);
     }
     __syncthreads();
-    if (bad) {
-      if (tid == 0) {
-        comp_sizes[b] = 0;
-        if (status) atomicOr(status, 1u);
-      }
-      __syncthreads();
-      continue;
-    }
-    for (int s = tid; s < K - 1; s += kCompThreads) {
-      const uint32_t e = sm.region_end[s];
-      uint8_t* p = dst + hdr + 4 * s;
-      p[0] = (uint8_t)e;
-      p[1] = (uint8_t)(e >> 8);
-      p[2] = (uint8_t)(e >> 16);
-      p[3] = (uint8_t)(e >> 24);
-    }
-    if (tid == 0) {
-      // slop bytes of region 0 that share an aligned word with the header
-      for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;
-      comp_sizes[b] = hdr_total + sm.region_end[K - 1];
-    }
-    // ---- phase 5: encode, one warp per stream
-    for (int s = warp; s < K; s += kCompWarps) {
-      uint32_t st, sz;
-      slice_geom(bn, K, s, st, sz);
-      const uint32_t e_off = hdr_total + sm.region_end[s];
-      const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
-      encode_stream_warp(sm.tab.enc, smem_u32(&sm.u.ring[warp][0]), src + st, sz, sm.stream_bits[s], dst, e_off, region, raw + n);
-    }
-    __syncthreads();
+    cur ^= 1;
   }
 }
 

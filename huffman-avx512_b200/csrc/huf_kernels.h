@@ -7,15 +7,15 @@
 namespace hufb200 {
 
 constexpr int kHistThreads = 512;
-#ifndef HUF_COMP_THREADS
-#define HUF_COMP_THREADS 256
-#endif
+// compress CTA: kWorkThreads worker threads (histogram, encode; must be 256 = one per bin) plus
+// one table-builder warp
 #ifndef HUF_COMP_MINB
 #define HUF_COMP_MINB 4
 #endif
-constexpr int kCompThreads = HUF_COMP_THREADS;
+constexpr int kWorkThreads = 256;
+constexpr int kCompThreads = kWorkThreads + 32;
 constexpr int kCompCtasPerSm = HUF_COMP_MINB;
-constexpr int kCompWarps = kCompThreads / 32;
+constexpr int kCompWarps = kWorkThreads / 32;  // worker warps
 constexpr int kDecMaxThreads = 256;
 
 size_t table_bytes();
