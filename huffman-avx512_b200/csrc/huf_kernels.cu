@@ -39,6 +39,18 @@ __device__ __forceinline__ uint32_t bins_reduce(const uint32_t* bins, int t) {
   for (int i = 0; i < 32; ++i) s += bins[(t << 5) + ((i + t) & 31)];
   return s;
 }
+// same, leaving the bins zeroed (the compress kernel keeps its bins / staging union all-zero
+// between phases, so neither needs a clearing pass)
+__device__ __forceinline__ uint32_t bins_reduce_clear(uint32_t* bins, int t) {
+  uint32_t s = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; ++i) {
+    uint32_t* p = bins + (t << 5) + ((i + t) & 31);
+    s += *p;
+    *p = 0;
+  }
+  return s;
+}
 
 // Accumulates the bytes [p, p+n) into the CTA's lane-private bins (all threads).
 // (t, nt): index of the calling thread among the nt threads that take part (whole warps).
@@ -449,20 +461,36 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
   const uint32_t e_al = e_off - r;
   const uint32_t s_al = (e_off - region + 3u) & ~3u;
   const uint32_t m_last = (e_al - s_al) >> 2;  // inclusive
-  uint32_t* out_lane = reinterpret_cast<uint32_t*>(dst + e_al) - lane;
   const uint32_t wtot = (uint32_t)((bits + 31) >> 5);
+  uint32_t* out = reinterpret_cast<uint32_t*>(dst + e_al) - lane;  // this lane's word of the current row
+  uint32_t sa = stage_base + 4u * (uint32_t)lane;
   uint32_t carry = 0;
-  for (uint32_t m0 = 0; m0 <= m_last; m0 += 32) {
+  uint32_t m0 = 0;
+  // full rows: 32 data words each, no predicates
+  for (; m0 + 32 <= wtot; m0 += 32) {
+    const uint32_t lo = lds_u32(sa);
+    sts_u32(sa, 0);
+    uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
+    if (lane == 0) hi = carry;
+    carry = __shfl_sync(0xffffffffu, lo, 31);
+    *out = __funnelshift_lc(lo, hi, sh);
+    out -= 32;
+    sa += 128;
+  }
+  // the rest: remaining data words, the partial word, padding and the zero slop
+  for (; m0 <= m_last; m0 += 32) {
     const uint32_t m = m0 + lane;
     uint32_t lo = 0;
     if (m < wtot) {
-      lo = lds_u32(stage_base + 4u * m);
-      sts_u32(stage_base + 4u * m, 0);
+      lo = lds_u32(sa);
+      sts_u32(sa, 0);
     }
     uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
     if (lane == 0) hi = carry;
     carry = __shfl_sync(0xffffffffu, lo, 31);
-    if (m <= m_last) *(out_lane - m0) = __funnelshift_lc(lo, hi, sh);
+    if (m <= m_last) *out = __funnelshift_lc(lo, hi, sh);
+    out -= 32;
+    sa += 128;
   }
   __syncwarp();
 }
@@ -479,11 +507,6 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
   const int lane = tid & 31;
   // slices short enough for the staged mode?  (uniform over the grid: depends on the geometry only)
   const bool staged = (block_size + (uint32_t)K - 1) / (uint32_t)K <= (uint32_t)kStageSlice;
-  {
-    uint4* rz = reinterpret_cast<uint4*>(&sm.u.stage[0][0]);
-    const int nz = (staged ? kCompWarps * kStageWords : kCompWarps * kRingWords) / 4;
-    for (int i = tid; i < nz; i += kWorkThreads) rz[i] = make_uint4(0, 0, 0, 0);
-  }
   // ---- header prefix (:799-808)
   const uint32_t hdr = tab.hdr_len;
   const uint32_t mask = tab.len_mask;
@@ -506,7 +529,6 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
   const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
   if (tid == 0)
     for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;  // slop bytes sharing a word with the header
-  worker_sync();  // staging zeroed
 
   if (staged) {
     // ---- staged mode: rounds of kCompWarps streams; encode into shared memory, then place.
@@ -624,13 +646,11 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
     return (uint32_t)((n - o) < (uint64_t)block_size ? (n - o) : (uint64_t)block_size);
   };
   // workers: histogram of block `blk` into sm.hist[slot]
+  // (the union is all-zero on entry and left all-zero)
   auto histogram_block = [&](uint32_t blk, int slot) {
-    uint4* z = reinterpret_cast<uint4*>(sm.u.bins);
-    for (int i = tid; i < 256 * 32 / 4; i += kWorkThreads) z[i] = make_uint4(0, 0, 0, 0);
-    worker_sync();
     bins_accumulate(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
     worker_sync();
-    sm.hist[slot][tid] = bins_reduce(sm.u.bins, tid);  // kWorkThreads == 256 bins
+    sm.hist[slot][tid] = bins_reduce_clear(sm.u.bins, tid);  // kWorkThreads == 256 bins
   };
   auto build_table = [&](int slot) {
     if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist[slot], &sm.tab[slot], &sm.sc);
@@ -638,6 +658,11 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
   };
 
   if (blockIdx.x >= n_blocks) return;
+  {  // the bins / staging union starts all-zero; every phase leaves it that way
+    uint4* z = reinterpret_cast<uint4*>(&sm.u);
+    for (int i = tid; i < (int)(sizeof(sm.u) / 16); i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
   // ---- prologue: first block's histogram and table (or the shared table into both slots)
   if (!builder && need_hist) histogram_block(blockIdx.x, 0);
   if (!own_tables) {
