@@ -281,12 +281,25 @@ __device__ __forceinline__ void stage_put(uint32_t stage_base, uint32_t pos, uin
   red_or_shared(a0 + 4u, shl_c(t, 32u - o));
 }
 
+// Up to 64 bits (eight symbols) at once: three words.  Bits of `code` above `len` are ignored.
+__device__ __forceinline__ void stage_put64(uint32_t stage_base, uint32_t pos, unsigned long long code, uint32_t len) {
+  unsigned long long t;
+  asm("shl.b64 %0, %1, %2;" : "=l"(t) : "l"(code), "r"(64u - len));  // left-aligned; len == 0 gives 0
+  const uint32_t hi = (uint32_t)(t >> 32), lo = (uint32_t)t;
+  const uint32_t o = pos & 31u;
+  const uint32_t a0 = stage_base + ((pos >> 3) & ~3u);
+  red_or_shared(a0, hi >> o);
+  red_or_shared(a0 + 4u, __funnelshift_r(lo, hi, o));
+  red_or_shared(a0 + 8u, shl_c(lo, 32u - o));
+}
+
 // Four table entries (first symbol first) -> the two pair codes and lengths.  c01 may carry
 // garbage above l01 bits (it always ends up left-aligned by a shift); c23 is clean.
+template <bool CLEAN = false>
 __device__ __forceinline__ void quad_code(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3, uint32_t& c01,
                                           uint32_t& l01, uint32_t& c23, uint32_t& l23) {
   const uint32_t l1 = e1 >> 16, l3 = e3 >> 16;
-  c01 = (e0 << l1) | (e1 & 0xffffu);
+  c01 = ((CLEAN ? (e0 & 0xffffu) : e0) << l1) | (e1 & 0xffffu);
   c23 = ((e2 & 0xffffu) << l3) | (e3 & 0xffffu);
   l01 = (e0 + e1) >> 16;
   l23 = (e2 + e3) >> 16;
@@ -411,16 +424,21 @@ __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* e
     uint32_t c01[4], l01[4], c23[4], l23[4];
     if (valid == 16) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        quad_code(enc[byte_of(w[j], 0)], enc[byte_of(w[j], 1)], enc[byte_of(w[j], 2)], enc[byte_of(w[j], 3)],
-                  c01[j], l01[j], c23[j], l23[j]);
+      for (int j = 0; j < 4; ++j) {
+        if (j & 1)  // second quad of an eight-symbol group: no stray bits above its length
+          quad_code<true>(enc[byte_of(w[j], 0)], enc[byte_of(w[j], 1)], enc[byte_of(w[j], 2)], enc[byte_of(w[j], 3)],
+                          c01[j], l01[j], c23[j], l23[j]);
+        else
+          quad_code(enc[byte_of(w[j], 0)], enc[byte_of(w[j], 1)], enc[byte_of(w[j], 2)], enc[byte_of(w[j], 3)],
+                    c01[j], l01[j], c23[j], l23[j]);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t e[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) e[i] = (uint32_t)(4 * j + i) < valid ? enc[byte_of(w[j], i)] : 0u;
-        quad_code(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
+        quad_code<true>(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
       }
     }
     uint32_t lq[4];
@@ -430,18 +448,28 @@ __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* e
     const uint32_t incl = warp_incl_scan(lane_len);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     // a symbol without a code makes `total` huge and lands here as an overflow, too
-    if (bitpos + total > (unsigned long long)(kStageWords - 1) * 32) over = true;
+    if (bitpos + total > (unsigned long long)(kStageWords - 2) * 32) over = true;  // puts touch up to 3 words
     if (!over) {
       uint32_t pos = (uint32_t)bitpos + (incl - lane_len);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (lq[j] <= 32) {
-          stage_put(stage_base, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
+      for (int h = 0; h < 4; h += 2) {
+        if (lq[h] <= 32 && lq[h + 1] <= 32) {  // almost always: one put for eight symbols
+          const uint32_t qa = (c01[h] << l23[h]) | c23[h];
+          const uint32_t qb = (c01[h + 1] << l23[h + 1]) | c23[h + 1];
+          stage_put64(stage_base, pos, ((unsigned long long)qa << lq[h + 1]) | qb, lq[h] + lq[h + 1]);
+          pos += lq[h] + lq[h + 1];
         } else {
-          stage_put(stage_base, pos, c01[j], l01[j]);
-          stage_put(stage_base, pos + l01[j], c23[j], l23[j]);
+#pragma unroll
+          for (int j = h; j < h + 2; ++j) {
+            if (lq[j] <= 32) {
+              stage_put(stage_base, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
+            } else {
+              stage_put(stage_base, pos, c01[j], l01[j]);
+              stage_put(stage_base, pos + l01[j], c23[j], l23[j]);
+            }
+            pos += lq[j];
+          }
         }
-        pos += lq[j];
       }
     }
     bitpos += total;
