@@ -20,11 +20,15 @@ namespace hufb200 {
 // touch the same bank or address, whatever the symbol distribution).
 // bins[sym * 32 + lane]
 // ===========================================================================
+// One `red.shared.add` per byte; the bin address is formed by a byte extract (PRMT) and one
+// shift-add (LEA) on the lane's 32-bit shared-space base.
 __device__ __forceinline__ void bins_add_word(uint32_t* bins_lane, uint32_t w) {
-  atomicAdd(bins_lane + ((w & 0xffu) << 5), 1u);
-  atomicAdd(bins_lane + (((w >> 8) & 0xffu) << 5), 1u);
-  atomicAdd(bins_lane + (((w >> 16) & 0xffu) << 5), 1u);
-  atomicAdd(bins_lane + ((w >> 24) << 5), 1u);
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(bins_lane);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t a = base + (__byte_perm(w, 0, 0x4440 + i) << 7);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory");
+  }
 }
 __device__ __forceinline__ void bins_add_vec(uint32_t* bins_lane, const uint4& v) {
   bins_add_word(bins_lane, v.x);
