@@ -1002,6 +1002,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     if (target > left) target = left;
     const uint32_t limit = target << 6;
     uint32_t rdo = (rd & 15) * 128;
+    const uint32_t rdo0 = rdo;
     uint32_t wofs = 0;  // byte offset of the next row word
     while (acc < limit) {
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
@@ -1012,7 +1013,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
       // everything below hangs off that chain
       uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
-      if ((e & (15u << 24)) == (12u << 24))  // a 12-bit code: the next bit picks one of the two siblings
+      if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))  // rare: a 12-bit code, the next bit picks the sibling
         v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
       ob |= v << sh;
       if ((acc ^ old) & 0x100u) {  // the symbol count crossed a multiple of 4: one row word is complete
@@ -1024,10 +1025,10 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
         hi = lo;
         lo = nxw;
         rdo = (rdo + 128) & (15 * 128);
-        ++rd;
         acc -= 32;
       }
     }
+    rd += ((rdo - rdo0) & (15 * 128)) >> 7;  // words consumed by this round (at most 6)
     if (target) {
       if (target == 16 && (((uintptr_t)outp) & 15) == 0) {
         uint4 v;
