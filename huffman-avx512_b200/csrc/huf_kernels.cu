@@ -1179,12 +1179,15 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
                             uint8_t* d_out, uint64_t slot_stride, uint32_t* d_sizes, const void* d_table,
                             int check_presence, uint32_t* d_status, int grid, cudaStream_t st) {
   if (n_blocks == 0) return cudaSuccess;
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(CompSmem));
+  // the attribute is per device: remember for which one it has been set (bit per ordinal)
+  static thread_local unsigned long long configured = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 64 || !((configured >> dev) & 1ull)) {
+    e = cudaFuncSetAttribute(k_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompSmem));
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev < 64) configured |= 1ull << dev;
   }
   k_compress_blocks<<<grid, kCompThreads, sizeof(CompSmem), st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride,
                                                    d_sizes, reinterpret_cast<const HufTable*>(d_table),
@@ -1203,11 +1206,9 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
   if (n_blocks == 0) return cudaSuccess;
   const int nthreads = ((K * bpc + 31) / 32) * 32;
   const size_t smem = decompress_smem_bytes(K, bpc);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {  // opt-in beyond the default limit (per device, so set whenever it is needed)
     cudaError_t e = cudaFuncSetAttribute(k_decompress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   const uint32_t grid = (n_blocks + bpc - 1) / bpc;
   k_decompress_blocks<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n,
