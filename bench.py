@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the multi-stream Huffman hot path (BASELINE.json config 2).
 
 A step = one pass of the hot path over one batch of synthetic input: compress (per-block
-histogram + table build + 32-stream encode) and then decompress (header parse + two-symbol
+histogram + table build + 32-stream encode) and then decompress (header parse + multi-symbol
 table + decode) of `--size` bytes per GPU (default 1 GiB) in 128 KiB blocks x 32 streams.
 `value` = raw bytes that went through the whole round trip per second, summed over ranks.
 

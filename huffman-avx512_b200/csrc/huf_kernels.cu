@@ -4,7 +4,8 @@
 //   k_build_table        canonical table from a 256 x u64 histogram (shared-table mode)
 //   k_make_table         same from a u32 histogram, dumping every field (ABI/table parity)
 //   k_compress_blocks    fused per-block histogram -> table -> stream lengths -> encode
-//   k_decompress_blocks  header parse -> two-symbol table -> one lane per stream decode
+//   k_decompress_blocks  header parse -> multi-symbol table (2 symbols x 12 bits = the reference's
+//                        Decoder2x; the kernel uses 3 symbols x 11 bits) -> one lane per stream decode
 //   k_dump_dtable        the decode kernel's table builder, for parity tests
 //   k_scan_sizes/k_pack  slot layout -> packed layout
 //
@@ -749,7 +750,7 @@ struct DecBlockInfo {
   uint32_t num_syms;
   uint32_t code_end[16];   // left-aligned (12-bit) end of the code range of each length
   uint32_t first_idx[16];  // index into sorted_syms of the first code of each length
-  uint8_t syms[256];       // sorted_syms, for the codes longer than the table's index
+  uint8_t syms[256];       // sorted_syms copied out of the header: the table builder reads shared memory
 };
 
 // Decode table over the next BITS bits of the stream, up to MAXSYM symbols per entry
@@ -809,7 +810,7 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
 
 constexpr int kDecBits = 11;  // the sibling-pair entries need exactly one unresolved bit
 constexpr int kDecEntries = 1 << kDecBits;
-constexpr int kDecRow = 20;  // bytes of output staging per lane: 16 per round + 2 spill-over
+constexpr int kDecRow = 20;  // bytes of output staging per lane: four row words per round + one for a partial word
 
 __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
                                     DecBlockInfo* bi) {
