@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Re-hosted report tooling (the reference's make_table.py:17-67).
+
+Turns our measurement files into (1) a google-benchmark-schema JSON
+(`{"benchmarks": [{"name": "BM_CompressBiased<::huffman::HuffmanCompressorB200<32>>",
+"bytes_per_second": ...}, ...]}`), which the reference's own make_table.py can read for the rows it
+knows (Scalar / AVX-512 Gather / AVX-512 Permute), and (2) the README-style Markdown table with the
+B200 rows next to the CPU rows measured in the same bench run.
+
+    python tools/report.py profiles/r1_bench.json profiles/r1_sweep.json [--json out.json]
+"""
+import argparse
+import json
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("bench_json")
+    ap.add_argument("sweep_json", nargs="?")
+    ap.add_argument("--json", default=None, help="write the google-benchmark-schema file here")
+    args = ap.parse_args()
+    bench = json.loads(open(args.bench_json).read().strip().splitlines()[-1])
+    k = bench["config"]["streams"]
+    rows = []  # (method, streams, compress B/s, decompress B/s, where)
+    gb = []
+    names = {"scalar": ("Scalar", "::huffman::HuffmanCompressorMulti"),
+             "avx512_gather": ("AVX-512 Gather", "::huffman::HuffmanCompressorAvxGather"),
+             "avx512_permute": ("AVX-512 Permute", "::huffman::HuffmanCompressorAvxPermute")}
+    cpu = bench.get("cpu_baseline", {})
+    for key, (label, cls) in names.items():
+        p = cpu.get("paths", {}).get(key)
+        if not p:
+            continue
+        c, d = p["compress_GBps"] * 1e9, p["decompress_GBps"] * 1e9
+        rows.append((label, k, c, d, f"host, {cpu.get('cores')} threads"))
+        gb.append({"name": f"BM_CompressBiased<{cls}<{k}>>", "bytes_per_second": c, "threads": cpu.get("cores")})
+        gb.append({"name": f"BM_DecompressBiased<{cls}<{k}>>", "bytes_per_second": d, "threads": cpu.get("cores")})
+    cells = [(k, bench["config"]["block_bytes"], bench["compress_GBps_per_gpu"] * 1e9, bench["decompress_GBps_per_gpu"] * 1e9)]
+    if args.sweep_json:
+        sw = json.load(open(args.sweep_json))
+        cells += [(c["k"], c["block"], c["comp_GBps"] * 1e9, c["dec_GBps"] * 1e9) for c in sw.get("config5", [])
+                  if c["block"] == bench["config"]["block_bytes"] and c["k"] != k]
+    for kk, blk, c, d in sorted(cells):
+        rows.append(("B200 (1 GPU, device-resident)", kk, c, d, f"{blk >> 10} KiB blocks"))
+        gb.append({"name": f"BM_CompressBiased<::huffman::HuffmanCompressorB200<{kk}>>", "bytes_per_second": c})
+        gb.append({"name": f"BM_DecompressBiased<::huffman::HuffmanCompressorB200<{kk}>>", "bytes_per_second": d})
+    rows.append(("Huff0", 4, None, None, cpu.get("huff0", "unavailable")))
+    if args.json:
+        json.dump({"context": {"source": args.bench_json, "metric": bench["metric"]}, "benchmarks": gb},
+                  open(args.json, "w"), indent=1)
+    mib = lambda x: "n/a" if x is None else f"{int(x / 2 ** 20)} MiB/s"
+    print("Method | Streams | Compress | Decompress | Where")
+    print("-------|---|---|---|---")
+    for m, s, c, d, w in rows:
+        print(f"{m} | {s} | {mib(c)} | {mib(d)} | {w}")
+
+
+if __name__ == "__main__":
+    main()
