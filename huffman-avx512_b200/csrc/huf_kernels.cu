@@ -413,7 +413,7 @@ __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* e
                                                                const uint8_t* lim) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
-  unsigned long long bitpos = 0;
+  uint32_t bitpos = 0;  // a staged stream is at most kStageSlice * 12 bits long
   bool over = false;
   // the next iteration's 16 symbols are requested one iteration ahead
   uint32_t noff = lane * 16;
@@ -453,9 +453,9 @@ __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* e
     const uint32_t incl = warp_incl_scan(lane_len);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     // a symbol without a code makes `total` huge and lands here as an overflow, too
-    if (bitpos + total > (unsigned long long)(kStageWords - 2) * 32) over = true;  // puts touch up to 3 words
+    if (bitpos + total > (uint32_t)(kStageWords - 2) * 32) over = true;  // puts touch up to 3 words
     if (!over) {
-      uint32_t pos = (uint32_t)bitpos + (incl - lane_len);
+      uint32_t pos = bitpos + (incl - lane_len);
 #pragma unroll
       for (int h = 0; h < 4; h += 2) {
         if (lq[h] <= 32 && lq[h + 1] <= 32) {  // almost always: one put for eight symbols
@@ -583,15 +583,19 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
       }
       worker_sync();
       const bool bad_now = sm.bad != 0;  // covers every stream up to this round
-      uint32_t my_end = 0, my_region = 0;
-      for (int t = s0; t < K && t < s0 + kCompWarps; ++t) {
-        const uint32_t reg = (uint32_t)((sm.stream_bits[t] + 7) >> 3) + kSlop;
-        run_end += reg;
-        if (t == s) {
-          my_end = run_end;
-          my_region = reg;
-        }
+      // region sizes of the round's streams: lane t of every warp takes stream s0 + t, a
+      // kCompWarps-wide shuffle scan gives the running ends
+      uint32_t reg = 0;
+      if (lane < kCompWarps && s0 + lane < K) reg = (uint32_t)((sm.stream_bits[s0 + lane] + 7) >> 3) + kSlop;
+      uint32_t incl = reg;
+#pragma unroll
+      for (int d = 1; d < kCompWarps; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
       }
+      const uint32_t my_region = __shfl_sync(0xffffffffu, reg, warp);
+      const uint32_t my_end = run_end + __shfl_sync(0xffffffffu, incl, warp);
+      run_end += __shfl_sync(0xffffffffu, incl, kCompWarps - 1);
       if (s < K) {
         if (lane == 0) sm.region_end[s] = my_end;
         if (!bad_now) {
