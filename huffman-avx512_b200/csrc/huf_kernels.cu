@@ -560,6 +560,13 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
     dst[i] = v;
   }
   const uint32_t hdr_total = hdr + 4u * (uint32_t)(K - 1);
+  // SliceSizes<K> (:98-108) without a division per stream
+  const uint32_t sl_q = bn / (uint32_t)K, sl_r = bn % (uint32_t)K;
+  auto geom = [&](int s, uint32_t& st, uint32_t& sz) {
+    const uint32_t us = (uint32_t)s;
+    sz = sl_q + (us < sl_r ? 1u : 0u);
+    st = us * sl_q + (us < sl_r ? us : sl_r);
+  };
   if (tid == 0)
     for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;  // slop bytes sharing a word with the header
 
@@ -576,7 +583,7 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
       unsigned long long bits = 0;
       const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
       if (s < K) {
-        slice_geom(bn, K, s, st, sz);
+        geom(s, st, sz);
         bits = encode_stream_staged_warp(tab.enc, stage_base, src + st, sz, &over, raw + n);
         if (bits > 12ull * sz) atomicOr(&sm.bad, 1u);  // a symbol without a code
         if (lane == 0) sm.stream_bits[s] = bits;
@@ -617,7 +624,7 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
     // ---- ring mode (long slices): per-stream bit totals first (:772-782)
     for (int s = warp; s < K; s += kCompWarps) {
       uint32_t st, sz;
-      slice_geom(bn, K, s, st, sz);
+      geom(s, st, sz);
       const unsigned long long bits = stream_length_warp(tab.enc, src + st, sz, &sm.bad, raw + n);
       if (lane == 0) sm.stream_bits[s] = bits;
     }
@@ -633,7 +640,7 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
     if (sm.bad == 0) {  // encode, one warp per stream
       for (int s = warp; s < K; s += kCompWarps) {
         uint32_t st, sz;
-        slice_geom(bn, K, s, st, sz);
+        geom(s, st, sz);
         const uint32_t e_off = hdr_total + sm.region_end[s];
         const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
         encode_stream_warp(tab.enc, smem_u32(&sm.u.ring[warp][0]), src + st, sz, sm.stream_bits[s], dst, e_off,
