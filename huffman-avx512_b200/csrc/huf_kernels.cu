@@ -821,7 +821,18 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
 
 constexpr int kDecBits = 11;  // the sibling-pair entries need exactly one unresolved bit
 constexpr int kDecEntries = 1 << kDecBits;
-constexpr int kDecRow = 20;  // bytes of output staging per lane: four row words per round + one for a partial word
+#ifndef HUF_DEC_LOOKUPS
+#define HUF_DEC_LOOKUPS 12
+#endif
+#ifndef HUF_DEC_ROW
+#define HUF_DEC_ROW 64
+#endif
+constexpr int kDecRow = HUF_DEC_ROW;          // bytes of output staging per lane: a ring of 16-byte chunks
+constexpr int kDecLookups = HUF_DEC_LOOKUPS;  // table lookups per lane per round (fixed: no lane waits for another inside a round)
+static_assert(kDecRow == 32 || kDecRow == 64, "ring of 2 or 4 chunks");
+static_assert(15 + 3 * kDecLookups < kDecRow, "a round must not overrun the unwritten part of the ring");
+constexpr uint32_t kRowWrap = (kDecRow / 4 - 1) * 128;
+constexpr int kDecEmits = (15 + 3 * kDecLookups) / 16;  // most complete chunks a round can leave behind
 
 __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
                                     DecBlockInfo* bi) {
@@ -967,7 +978,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // shared-space addresses, kept in registers
   const uint32_t t_addr = smem_u32(tables + (size_t)(lb < bpc ? lb : 0) * kDecEntries);
   const uint32_t col = smem_u32(region) + (uint32_t)warp * (16 * 32 * 4) + 4u * (uint32_t)lane;  // word i at col + (i & 15) * 128
-  // output staging: word j (4 symbols) of this lane at row + j * 128 -- lane-private bank, conflict-free
+  // output staging ring: word j (4 symbols) of this lane at row + (j & 15) * 128 -- lane-private bank
   const uint32_t row = smem_u32(region) + (uint32_t)nwarps * (16 * 32 * 4) + (uint32_t)warp * (32 * kDecRow) + 4u * (uint32_t)lane;
   // make the three addresses opaque so that they stay in registers instead of being recomputed
   // from tid / %ctaid inside the lookup loop
@@ -993,12 +1004,24 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t lo = lds_u32(col + ((rd + 1) & 15) * 128);
   rd += 2;
 
-  // The first round of a lane whose slice does not start on a 16-byte boundary is a short one
-  // that brings it there, so that every later full round is one aligned 128-bit store.
-  uint32_t head = (uint32_t)((16 - ((uintptr_t)outp & 15)) & 15);
-  while (__any_sync(0xffffffffu, left != 0)) {
-    // Top up the ring: a round consumes at most 7 words.  The chunk stored now was requested
-    // at the previous top-up, so its latency is hidden unless the stream runs at > 8 bits/symbol.
+  // Rounds of kDecLookups lookups per lane.  Every lane does the same number of lookups per
+  // round (the symbols they yield differ, 1..3 each); the symbols go into a 64-byte ring per lane
+  // whose byte positions are congruent to the output addresses mod 16, so every complete 16-byte
+  // ring chunk leaves as one aligned 128-bit store.  acc: bits 0..5 = bits consumed from the
+  // window, bits 6.. = ring write position in bytes (starts at the slice's misalignment h0).
+  const uint32_t h0 = (uint32_t)((uintptr_t)outp & 15);
+  uint8_t* const out_al = outp - h0;                   // 16-byte aligned; ring byte p <-> out_al[p]
+  const uint32_t end_pos = h0 + left;                   // ring position one past the last symbol
+  const uint32_t end_acc = end_pos << 6;
+  const uint32_t full_chunks = end_pos >> 4;            // chunks that lie entirely inside the slice
+  acc |= h0 << 6;
+  uint32_t wofs = (h0 >> 2) * 128;                      // byte offset of the ring word being filled
+  uint32_t chunk = 0;                                   // next 16-byte chunk to write out
+  uint32_t rdo = (rd & 15) * 128;
+  while (__any_sync(0xffffffffu, acc < end_acc)) {
+    // Top up the input ring: a round consumes at most 4 words.  The chunk stored now was
+    // requested at the previous top-up, so its latency is hidden unless the stream runs at
+    // more than 8 bits/symbol.
     while (staged - rd < 11) {
       const uint32_t o = (staged & 15) * 128;  // staged % 4 == 0: the four words do not wrap
       sts_u32(col + o, pf.w);
@@ -1009,63 +1032,63 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
       ++cidx;
     }
-    uint32_t target = head ? head : 16u;
-    head = 0;
-    if (target > left) target = left;
-    const uint32_t limit = target << 6;
-    uint32_t rdo = (rd & 15) * 128;
     const uint32_t rdo0 = rdo;
-    uint32_t wofs = 0;  // byte offset of the next row word
-    while (acc < limit) {
-      const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
-      const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
-      const uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
-      const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (symbols pending in ob)
-      const uint32_t old = acc;
-      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
-      // everything below hangs off that chain
-      uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
-      if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))  // rare: a 12-bit code, the next bit picks the sibling
-        v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
-      ob |= v << sh;
-      if ((acc ^ old) & 0x100u) {  // the symbol count crossed a multiple of 4: one row word is complete
-        sts_u32(row + wofs, ob);
-        wofs += 128;
-        ob = shr_c(v, 32u - sh);
-      }
-      if (acc & 32u) {
-        hi = lo;
-        lo = nxw;
-        rdo = (rdo + 128) & (15 * 128);
-        acc -= 32;
-      }
-    }
-    rd += ((rdo - rdo0) & (15 * 128)) >> 7;  // words consumed by this round (at most 6)
-    if (target) {
-      if (target == 16 && (((uintptr_t)outp) & 15) == 0) {
-        uint4 v;
-        v.x = lds_u32(row + 0);
-        v.y = lds_u32(row + 128);
-        v.z = lds_u32(row + 256);
-        v.w = lds_u32(row + 384);
-        *reinterpret_cast<uint4*>(outp) = v;
-      } else {
-        sts_u32(row + wofs, ob);  // partial word
-        for (uint32_t i = 0; i < target; ++i) outp[i] = (uint8_t)lds_u8(row + (i >> 2) * 128 + (i & 3));
-        if (target != 16) {  // short round: re-base the (at most 2) symbols decoded beyond it into ob
-          const uint32_t extra = (acc >> 6) - target;
-          ob = 0;
-          for (uint32_t i = 0; i < extra; ++i) {
-            const uint32_t j = target + i;
-            ob |= lds_u8(row + (j >> 2) * 128 + (j & 3)) << (8 * i);
-          }
+#pragma unroll
+    for (int it = 0; it < kDecLookups; ++it) {
+      if (acc < end_acc) {
+        const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
+        const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
+        const uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
+        const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (position in the ring word being filled)
+        const uint32_t old = acc;
+        acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
+        // everything below hangs off that chain
+        uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
+        if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))  // rare: a 12-bit code, the next bit picks the sibling
+          v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
+        ob |= v << sh;
+        if ((acc ^ old) & 0x100u) {  // the write position crossed a multiple of 4: one ring word is complete
+          sts_u32(row + wofs, ob);
+          wofs = (wofs + 128) & kRowWrap;
+          ob = shr_c(v, 32u - sh);
+        }
+        if (acc & 32u) {
+          hi = lo;
+          lo = nxw;
+          rdo = (rdo + 128) & (15 * 128);
+          acc -= 32;
         }
       }
-      outp += target;
-      left -= target;
-      // symbols decoded beyond this round (at most 2) stay in ob and open the next round
-      acc -= target << 6;
     }
+    rd += ((rdo - rdo0) & (15 * 128)) >> 7;  // words consumed by this round (at most 4)
+    // write out the complete chunks (a round adds at most 3 * kDecLookups bytes)
+#pragma unroll
+    for (int t = 0; t < kDecEmits; ++t) {
+      uint32_t avail = acc >> 10;  // complete chunks by write position ...
+      if (avail > full_chunks) avail = full_chunks;  // ... that do not reach past the slice
+      if (chunk < avail) {
+        const uint32_t w0 = (chunk * 512) & kRowWrap;  // four ring words per chunk
+        uint4 v;
+        v.x = lds_u32(row + w0);
+        v.y = lds_u32(row + w0 + 128);
+        v.z = lds_u32(row + w0 + 256);
+        v.w = lds_u32(row + w0 + 384);
+        if (chunk == 0 && h0 != 0) {  // the slice starts inside this chunk
+          const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+          for (uint32_t i = h0; i < 16; ++i) out_al[i] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
+        } else {
+          *reinterpret_cast<uint4*>(out_al + 16 * (size_t)chunk) = v;
+        }
+        ++chunk;
+      }
+    }
+  }
+  // tail: the bytes of the last, partial chunk
+  if (left) {
+    sts_u32(row + wofs, ob);  // the ring word still being filled
+    uint32_t p = 16 * chunk;
+    if (p < h0) p = h0;
+    for (; p < end_pos; ++p) out_al[p] = (uint8_t)lds_u8(row + (((p >> 2) * 128) & kRowWrap) + (p & 3));
   }
 }
 
