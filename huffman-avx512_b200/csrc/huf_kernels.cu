@@ -831,6 +831,7 @@ constexpr int kDecRow = HUF_DEC_ROW;          // bytes of output staging per lan
 constexpr int kDecLookups = HUF_DEC_LOOKUPS;  // table lookups per lane per round (fixed: no lane waits for another inside a round)
 static_assert(kDecRow == 32 || kDecRow == 64, "ring of 2 or 4 chunks");
 static_assert(15 + 3 * kDecLookups < kDecRow, "a round must not overrun the unwritten part of the ring");
+static_assert(12 * kDecLookups + 31 < 6 * 32, "a round must not consume more than 5 input words");
 constexpr uint32_t kRowWrap = (kDecRow / 4 - 1) * 128;
 constexpr int kDecEmits = (15 + 3 * kDecLookups) / 16;  // most complete chunks a round can leave behind
 
@@ -967,9 +968,9 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     left = sz;
     outp = raw + (uint64_t)b * block_size + st;
     const uintptr_t end_addr = (uintptr_t)(blk + bi->payload_off) + e_off;  // exclusive
-    e16 = (end_addr + 15) & ~(uintptr_t)15;
+    e16 = (end_addr + 31) & ~(uintptr_t)31;  // input is fetched in whole 32-byte sectors
     const uint32_t pad = (uint32_t)(e16 - end_addr);
-    lo_lim = (uintptr_t)blk & ~(uintptr_t)15;
+    lo_lim = (uintptr_t)blk & ~(uintptr_t)31;
     rd = pad >> 2;
     acc = 8 * (pad & 3);
   }
@@ -984,22 +985,33 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // from tid / %ctaid inside the lookup loop
   asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
 
-  // prime: stage 3 chunks (12 words) and keep the next one in registers
-  uint4 pf;
-  {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const uint4 ch = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
-      sts_u32(col + ((staged + 0) & 15) * 128, ch.w);
-      sts_u32(col + ((staged + 1) & 15) * 128, ch.z);
-      sts_u32(col + ((staged + 2) & 15) * 128, ch.y);
-      sts_u32(col + ((staged + 3) & 15) * 128, ch.x);
-      staged += 4;
-      ++cidx;
-    }
-    pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
+  // prime: stage two 32-byte sectors (the whole 16-word ring) and keep the next one in registers.
+  // Each top-up takes a full sector, so the kernel does not depend on L1 to serve the other half
+  // of a sector later (L1 is nearly gone once shared memory is carved out for the tables).
+  uint4 pf0, pf1;  // pf1 = upper 16 bytes (earlier in the stream), pf0 = lower 16 bytes
+  auto load_sector = [&]() {
+    const uintptr_t a = e16 - 32 * (uintptr_t)(cidx + 1);
+    pf1 = active ? ld_chunk(a + 16, lo_lim) : make_uint4(0, 0, 0, 0);
+    pf0 = active ? ld_chunk(a, lo_lim) : make_uint4(0, 0, 0, 0);
     ++cidx;
-  }
+  };
+  auto stage_sector = [&]() {
+    const uint32_t o = (staged & 15) * 128;  // staged % 8 == 0: the eight words do not wrap
+    sts_u32(col + o, pf1.w);
+    sts_u32(col + o + 128, pf1.z);
+    sts_u32(col + o + 256, pf1.y);
+    sts_u32(col + o + 384, pf1.x);
+    sts_u32(col + o + 512, pf0.w);
+    sts_u32(col + o + 640, pf0.z);
+    sts_u32(col + o + 768, pf0.y);
+    sts_u32(col + o + 896, pf0.x);
+    staged += 8;
+  };
+  load_sector();
+  stage_sector();
+  load_sector();
+  stage_sector();
+  load_sector();
   uint32_t hi = lds_u32(col + (rd & 15) * 128);
   uint32_t lo = lds_u32(col + ((rd + 1) & 15) * 128);
   rd += 2;
@@ -1019,18 +1031,11 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t chunk = 0;                                   // next 16-byte chunk to write out
   uint32_t rdo = (rd & 15) * 128;
   while (__any_sync(0xffffffffu, acc < end_acc)) {
-    // Top up the input ring: a round consumes at most 4 words.  The chunk stored now was
-    // requested at the previous top-up, so its latency is hidden unless the stream runs at
-    // more than 8 bits/symbol.
-    while (staged - rd < 11) {
-      const uint32_t o = (staged & 15) * 128;  // staged % 4 == 0: the four words do not wrap
-      sts_u32(col + o, pf.w);
-      sts_u32(col + o + 128, pf.z);
-      sts_u32(col + o + 256, pf.y);
-      sts_u32(col + o + 384, pf.x);
-      staged += 4;
-      pf = active ? ld_chunk(e16 - 16 * (uintptr_t)(cidx + 1), lo_lim) : make_uint4(0, 0, 0, 0);
-      ++cidx;
+    // Top up the input ring: a round consumes at most 5 words (+1 looked ahead).  The sector
+    // stored now was requested at the previous top-up, so its latency is hidden.
+    if (staged - rd <= 8) {  // room for a sector; afterwards at least 9 words are staged
+      stage_sector();
+      load_sector();
     }
     const uint32_t rdo0 = rdo;
 #pragma unroll
