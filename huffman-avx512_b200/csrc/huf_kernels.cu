@@ -877,6 +877,13 @@ __device__ __forceinline__ uint4 ld_chunk(uintptr_t addr, uintptr_t lo_lim) {
   if (addr >= lo_lim) return *reinterpret_cast<const uint4*>(addr);
   return make_uint4(0, 0, 0, 0);
 }
+// read-only data (the decode table inside the lookup loop): not volatile, no memory clobber, so
+// the compiler may schedule it across the loop's other shared-memory traffic
+__device__ __forceinline__ uint32_t lds_u32_ro(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -1040,29 +1047,30 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     const uint32_t rdo0 = rdo;
 #pragma unroll
     for (int it = 0; it < kDecLookups; ++it) {
-      if (acc < end_acc) {
-        const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
-        const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
-        const uint32_t e = lds_u32(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
-        const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (position in the ring word being filled)
-        const uint32_t old = acc;
-        acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
-        // everything below hangs off that chain
-        uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
-        if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))  // rare: a 12-bit code, the next bit picks the sibling
-          v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
-        ob |= v << sh;
-        if ((acc ^ old) & 0x100u) {  // the write position crossed a multiple of 4: one ring word is complete
-          sts_u32(row + wofs, ob);
-          wofs = (wofs + 128) & kRowWrap;
-          ob = shr_c(v, 32u - sh);
-        }
-        if (acc & 32u) {
-          hi = lo;
-          lo = nxw;
-          rdo = (rdo + 128) & (15 * 128);
-          acc -= 32;
-        }
+      // Straight-line body (no branch per lookup, so consecutive lookups can overlap): a lane that
+      // has all its symbols sees an all-zero entry, which changes nothing below.
+      const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
+      const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
+      uint32_t e = lds_u32_ro(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
+      if (acc >= end_acc) e = 0;
+      const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (position in the ring word being filled)
+      const uint32_t old = acc;
+      acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
+      // everything below hangs off that chain
+      uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
+      if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))  // rare: a 12-bit code, the next bit picks the sibling
+        v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
+      ob |= v << sh;
+      if ((acc ^ old) & 0x100u) {  // the write position crossed a multiple of 4: one ring word is complete
+        sts_u32(row + wofs, ob);
+        wofs = (wofs + 128) & kRowWrap;
+        ob = shr_c(v, 32u - sh);
+      }
+      if (acc & 32u) {
+        hi = lo;
+        lo = nxw;
+        rdo = (rdo + 128) & (15 * 128);
+        acc -= 32;
       }
     }
     rd += ((rdo - rdo0) & (15 * 128)) >> 7;  // words consumed by this round (at most 4)
