@@ -136,16 +136,29 @@ constexpr size_t kMaxBlock = (size_t)1 << 30;  // offsets are 32-bit inside a bu
 constexpr uint32_t kMagic = 0x32424648u;        // "HFB2"
 constexpr size_t kContainerHeader = 32;
 
-// Blocks per decode CTA: about 96 lanes (3 warps for K = 32; measured best on B200) so that the
-// per-CTA shared-memory reserve is amortised without losing resident CTAs to granularity.
+// Blocks per decode CTA: one lane per stream, so bpc * k lanes.  About 64 lanes (2 warps for
+// K = 32) measured best on B200: enough CTAs stay resident while the shared-memory total stays
+// under the 196 KiB carve-out, which leaves the L1 its larger size.  Among 64..128 lanes the
+// count that fills its warps best wins (K = 48: two blocks = three full warps).
 #ifndef HUF_DEC_LANES
-#define HUF_DEC_LANES 96
+#define HUF_DEC_LANES 64
 #endif
 int decode_bpc(int k) {
-  int bpc = HUF_DEC_LANES / k;
-  if (bpc < 1) bpc = 1;
-  if (bpc > 16) bpc = 16;
-  return bpc;
+  int best = 1;
+  double best_util = 0.0;
+  for (int b = 1; b <= 16; ++b) {
+    const int lanes = b * k;
+    if (b > 1 && lanes > 2 * HUF_DEC_LANES) break;
+    const double util = (double)lanes / (double)((lanes + 31) / 32 * 32);
+    const bool big_enough = lanes >= HUF_DEC_LANES;
+    // until the target size is reached more lanes are always better; beyond it only a better fill counts
+    if (b == 1 || util > best_util + 1e-9 || (best * k < HUF_DEC_LANES && util >= best_util - 0.02)) {
+      best = b;
+      best_util = util;
+    }
+    if (big_enough && util > 0.999) break;
+  }
+  return best;
 }
 
 int compress_grid(uint32_t n_blocks, int sms) {

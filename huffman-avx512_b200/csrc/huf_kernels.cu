@@ -10,6 +10,8 @@
 //   k_scan_sizes/k_pack  slot layout -> packed layout
 //
 // Reference behaviour: ahartik/huffman-avx512 codec/huffman.cpp, codec/histogram.cpp.
+#include <type_traits>
+
 #include "huf_device.cuh"
 #include "huf_kernels.h"
 
@@ -822,18 +824,19 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
 constexpr int kDecBits = 11;  // the sibling-pair entries need exactly one unresolved bit
 constexpr int kDecEntries = 1 << kDecBits;
 #ifndef HUF_DEC_LOOKUPS
-#define HUF_DEC_LOOKUPS 12
+#define HUF_DEC_LOOKUPS 10
 #endif
 #ifndef HUF_DEC_ROW
 #define HUF_DEC_ROW 64
 #endif
-constexpr int kDecRow = HUF_DEC_ROW;          // bytes of output staging per lane: a ring of 16-byte chunks
+constexpr int kDecRow = HUF_DEC_ROW;          // bytes of output staging per lane: a ring of 32-byte chunks
+constexpr int kDecChunk = 32;                 // one 256-bit store
 constexpr int kDecLookups = HUF_DEC_LOOKUPS;  // table lookups per lane per round (fixed: no lane waits for another inside a round)
-static_assert(kDecRow == 32 || kDecRow == 64, "ring of 2 or 4 chunks");
-static_assert(15 + 3 * kDecLookups < kDecRow, "a round must not overrun the unwritten part of the ring");
+static_assert(kDecRow == 64 || kDecRow == 128, "ring of 2 or 4 chunks");
+static_assert(kDecChunk - 1 + 3 * kDecLookups < kDecRow, "a round must not overrun the unwritten part of the ring");
 static_assert(12 * kDecLookups + 31 < 6 * 32, "a round must not consume more than 5 input words");
 constexpr uint32_t kRowWrap = (kDecRow / 4 - 1) * 128;
-constexpr int kDecEmits = (15 + 3 * kDecLookups) / 16;  // most complete chunks a round can leave behind
+constexpr int kDecEmits = (kDecChunk - 1 + 3 * kDecLookups) / kDecChunk;  // most complete chunks a round can leave behind
 
 __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
                                     DecBlockInfo* bi) {
@@ -873,9 +876,28 @@ __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int 
   bi->ok = 1;
 }
 
-__device__ __forceinline__ uint4 ld_chunk(uintptr_t addr, uintptr_t lo_lim) {
-  if (addr >= lo_lim) return *reinterpret_cast<const uint4*>(addr);
-  return make_uint4(0, 0, 0, 0);
+// 32 bytes per lane in one instruction (256-bit global accesses, sm_100+): a lane's sector or
+// output chunk costs one trip through the load/store pipe instead of two
+struct Sector {
+  uint32_t w[8];
+};
+__device__ __forceinline__ Sector ld_sector(uintptr_t addr, uintptr_t lo_lim) {
+  Sector s;
+  if (addr >= lo_lim) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]), "=r"(s.w[4]), "=r"(s.w[5]), "=r"(s.w[6]),
+                   "=r"(s.w[7])
+                 : "l"(addr));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.w[i] = 0;
+  }
+  return s;
+}
+__device__ __forceinline__ void st_chunk32(uint8_t* addr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 // read-only data (the decode table inside the lookup loop): not volatile, no memory clobber, so
 // the compiler may schedule it across the loop's other shared-memory traffic
@@ -891,6 +913,14 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
+}
+
+// table base + 4 * index as one multiply-add: it runs on the FMA pipe, next to the lookup loop's
+// many ALU-pipe shifts and logic ops
+__device__ __forceinline__ uint32_t entry_addr(uint32_t base, uint32_t idx) {
+  uint32_t a;
+  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(idx), "r"(base));
+  return a;
 }
 
 // per-CTA scratch behind the tables: the T1 build scratch, later the lane rings and output rows
@@ -995,23 +1025,16 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // prime: stage two 32-byte sectors (the whole 16-word ring) and keep the next one in registers.
   // Each top-up takes a full sector, so the kernel does not depend on L1 to serve the other half
   // of a sector later (L1 is nearly gone once shared memory is carved out for the tables).
-  uint4 pf0, pf1;  // pf1 = upper 16 bytes (earlier in the stream), pf0 = lower 16 bytes
+  Sector pf = {};  // words in address order: the stream runs from w[7] down to w[0]
   auto load_sector = [&]() {
     const uintptr_t a = e16 - 32 * (uintptr_t)(cidx + 1);
-    pf1 = active ? ld_chunk(a + 16, lo_lim) : make_uint4(0, 0, 0, 0);
-    pf0 = active ? ld_chunk(a, lo_lim) : make_uint4(0, 0, 0, 0);
+    if (active) pf = ld_sector(a, lo_lim);
     ++cidx;
   };
   auto stage_sector = [&]() {
     const uint32_t o = (staged & 15) * 128;  // staged % 8 == 0: the eight words do not wrap
-    sts_u32(col + o, pf1.w);
-    sts_u32(col + o + 128, pf1.z);
-    sts_u32(col + o + 256, pf1.y);
-    sts_u32(col + o + 384, pf1.x);
-    sts_u32(col + o + 512, pf0.w);
-    sts_u32(col + o + 640, pf0.z);
-    sts_u32(col + o + 768, pf0.y);
-    sts_u32(col + o + 896, pf0.x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sts_u32(col + o + 128 * i, pf.w[7 - i]);
     staged += 8;
   };
   load_sector();
@@ -1028,43 +1051,38 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // whose byte positions are congruent to the output addresses mod 16, so every complete 16-byte
   // ring chunk leaves as one aligned 128-bit store.  acc: bits 0..5 = bits consumed from the
   // window, bits 6.. = ring write position in bytes (starts at the slice's misalignment h0).
-  const uint32_t h0 = (uint32_t)((uintptr_t)outp & 15);
-  uint8_t* const out_al = outp - h0;                   // 16-byte aligned; ring byte p <-> out_al[p]
+  const uint32_t h0 = (uint32_t)((uintptr_t)outp & (kDecChunk - 1));
+  uint8_t* const out_al = outp - h0;                   // chunk-aligned; ring byte p <-> out_al[p]
   const uint32_t end_pos = h0 + left;                   // ring position one past the last symbol
   const uint32_t end_acc = end_pos << 6;
-  const uint32_t full_chunks = end_pos >> 4;            // chunks that lie entirely inside the slice
+  const uint32_t full_chunks = end_pos >> 5;            // chunks that lie entirely inside the slice
   acc |= h0 << 6;
   uint32_t wofs = (h0 >> 2) * 128;                      // byte offset of the ring word being filled
-  uint32_t chunk = 0;                                   // next 16-byte chunk to write out
+  uint32_t chunk = 0;                                   // next 32-byte chunk to write out
   uint32_t rdo = (rd & 15) * 128;
-  while (__any_sync(0xffffffffu, acc < end_acc)) {
-    // Top up the input ring: a round consumes at most 5 words (+1 looked ahead).  The sector
-    // stored now was requested at the previous top-up, so its latency is hidden.
-    if (staged - rd <= 8) {  // room for a sector; afterwards at least 9 words are staged
-      stage_sector();
-      load_sector();
-    }
-    const uint32_t rdo0 = rdo;
+  // One round = kDecLookups straight-line lookups (no branch per lookup, so consecutive lookups
+  // overlap).  CHECKED rounds are the last few of a warp, when some lane may run out of symbols:
+  // a lane that has them all sees an all-zero entry, which changes nothing.
+  auto lookups = [&](auto checked) {
 #pragma unroll
     for (int it = 0; it < kDecLookups; ++it) {
-      // Straight-line body (no branch per lookup, so consecutive lookups can overlap): a lane that
-      // has all its symbols sees an all-zero entry, which changes nothing below.
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
       const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
-      uint32_t e = lds_u32_ro(t_addr + ((win >> (30 - kDecBits)) & ((kDecEntries - 1) << 2)));
-      if (acc >= end_acc) e = 0;
+      uint32_t e = lds_u32_ro(entry_addr(t_addr, win >> (32 - kDecBits)));
+      if (decltype(checked)::value && acc >= end_acc) e = 0;
       const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (position in the ring word being filled)
       const uint32_t old = acc;
       acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
       // everything below hangs off that chain
       uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
-      if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))  // rare: a 12-bit code, the next bit picks the sibling
+      // rare: a 12-bit code ("12 bits consumed" marks it): the next bit picks one of the two siblings
+      if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))
         v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
       ob |= v << sh;
       if ((acc ^ old) & 0x100u) {  // the write position crossed a multiple of 4: one ring word is complete
         sts_u32(row + wofs, ob);
         wofs = (wofs + 128) & kRowWrap;
-        ob = shr_c(v, 32u - sh);
+        ob = __funnelshift_l(v, 0, sh);  // the symbols that did not fit: v >> (32 - sh), 0 for sh == 0
       }
       if (acc & 32u) {
         hi = lo;
@@ -1073,24 +1091,42 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
         acc -= 32;
       }
     }
+  };
+  // a lane is "far" from its end if a whole round cannot exhaust it; lanes without a stream run
+  // harmless lookups on a zero window in unchecked rounds (private rings, nothing is emitted)
+  const uint32_t far_acc = end_acc >= ((3u * kDecLookups) << 6) ? end_acc - ((3u * kDecLookups) << 6) : 0u;
+  const bool no_stream = !active || left == 0;
+  while (__any_sync(0xffffffffu, acc < end_acc)) {
+    // Top up the input ring: a round consumes at most 5 words (+1 looked ahead).  The sector
+    // stored now was requested at the previous top-up, so its latency is hidden.
+    if (staged - rd <= 8) {  // room for a sector; afterwards at least 9 words are staged
+      stage_sector();
+      load_sector();
+    }
+    const uint32_t rdo0 = rdo;
+    if (__all_sync(0xffffffffu, no_stream || acc <= far_acc)) lookups(std::false_type{});
+    else lookups(std::true_type{});
     rd += ((rdo - rdo0) & (15 * 128)) >> 7;  // words consumed by this round (at most 4)
     // write out the complete chunks (a round adds at most 3 * kDecLookups bytes)
 #pragma unroll
     for (int t = 0; t < kDecEmits; ++t) {
-      uint32_t avail = acc >> 10;  // complete chunks by write position ...
+      uint32_t avail = acc >> 11;  // complete chunks by write position ...
       if (avail > full_chunks) avail = full_chunks;  // ... that do not reach past the slice
       if (chunk < avail) {
-        const uint32_t w0 = (chunk * 512) & kRowWrap;  // four ring words per chunk
-        uint4 v;
-        v.x = lds_u32(row + w0);
-        v.y = lds_u32(row + w0 + 128);
-        v.z = lds_u32(row + w0 + 256);
-        v.w = lds_u32(row + w0 + 384);
+        const uint32_t w0 = (chunk * 1024) & kRowWrap;  // eight ring words per chunk
+        uint32_t v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = lds_u32(row + w0 + 128 * i);
         if (chunk == 0 && h0 != 0) {  // the slice starts inside this chunk
-          const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-          for (uint32_t i = h0; i < 16; ++i) out_al[i] = (uint8_t)(wv[i >> 2] >> (8 * (i & 3)));
+          for (uint32_t i = h0; i < (uint32_t)kDecChunk; ++i) {
+            uint32_t w = v[0];
+#pragma unroll
+            for (int j = 1; j < 8; ++j)
+              if ((i >> 2) == (uint32_t)j) w = v[j];
+            out_al[i] = (uint8_t)(w >> (8 * (i & 3)));
+          }
         } else {
-          *reinterpret_cast<uint4*>(out_al + 16 * (size_t)chunk) = v;
+          st_chunk32(out_al + kDecChunk * (size_t)chunk, v);
         }
         ++chunk;
       }
@@ -1099,7 +1135,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // tail: the bytes of the last, partial chunk
   if (left) {
     sts_u32(row + wofs, ob);  // the ring word still being filled
-    uint32_t p = 16 * chunk;
+    uint32_t p = kDecChunk * chunk;
     if (p < h0) p = h0;
     for (; p < end_pos; ++p) out_al[p] = (uint8_t)lds_u8(row + (((p >> 2) * 128) & kRowWrap) + (p & 3));
   }
