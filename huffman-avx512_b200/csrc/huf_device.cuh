@@ -50,11 +50,20 @@ __device__ __forceinline__ void slice_geom(uint32_t n, int K, int s, uint32_t& s
   start = us * q + (us < r ? us : r);
 }
 
+// Inclusive warp scan.  shfl.up reports through its predicate whether the source lane exists, so a
+// step is two instructions (shuffle, predicated add) and needs no lane-id compares.
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-    if (lane_id() >= d) v += t;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 t;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+        "@p add.u32 %0, %0, t;\n\t"
+        "}"
+        : "+r"(v)
+        : "r"(d));
   }
   return v;
 }

@@ -10,6 +10,7 @@
 //   k_scan_sizes/k_pack  slot layout -> packed layout
 //
 // Reference behaviour: ahartik/huffman-avx512 codec/huffman.cpp, codec/histogram.cpp.
+#include <atomic>
 #include <type_traits>
 
 #include "huf_device.cuh"
@@ -166,6 +167,7 @@ struct CompSmem {
   unsigned long long stream_bits[kMaxK];
   uint32_t region_end[kMaxK];  // cumulative end offsets relative to the payload start (:772-786)
   uint32_t bad;
+  uint32_t blk_new, blk_new2;  // block indices just drawn from the launch's counter
 };
 
 __device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) {  // shift >= 32 gives 0
@@ -189,6 +191,21 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// table base + 4 * index as one multiply-add: it runs on the FMA pipe, next to the lookup loop's
+// many ALU-pipe shifts and logic ops
+__device__ __forceinline__ uint32_t entry_addr(uint32_t base, uint32_t idx) {
+  uint32_t a;
+  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(idx), "r"(base));
+  return a;
+}
+
+// read-only data (the decode table inside the lookup loop): not volatile, no memory clobber, so
+// the compiler may schedule it across the loop's other shared-memory traffic
+__device__ __forceinline__ uint32_t lds_u32_ro(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 // byte i of w, zero-extended (one PRMT)
 __device__ __forceinline__ uint32_t byte_of(uint32_t w, int i) { return __byte_perm(w, 0, 0x4440 + i); }
@@ -410,44 +427,18 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_bas
 // Staged mode, step 1: encode the whole stream into the warp's linear staging buffer (zeroed by
 // the previous copy-out).  Returns the stream's bit total; *overflow is set when it does not fit
 // (then only the count is valid and the caller falls back to the ring path).
-__device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* enc, uint32_t stage_base,
+// enc_addr: shared-space address of the encode table (entry = code | len << 16).
+__device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr, uint32_t stage_base,
                                                                const uint8_t* sp, uint32_t sz, bool* overflow,
                                                                const uint8_t* lim) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
   uint32_t bitpos = 0;  // a staged stream is at most kStageSlice * 12 bits long
   bool over = false;
-  // the next iteration's 16 symbols are requested one iteration ahead
-  uint32_t noff = lane * 16;
-  uint32_t nvalid = noff < sz ? (sz - noff < 16 ? sz - noff : 16) : 0;
-  uint4 vnext = load16(sp, noff, nvalid, aligned, lim);
-  for (uint32_t base = 0; base < sz; base += 512) {
-    const uint4 v = vnext;
-    const uint32_t valid = nvalid;
-    noff += 512;
-    nvalid = noff < sz ? (sz - noff < 16 ? sz - noff : 16) : 0;
-    if (base + 512 < sz) vnext = load16(sp, noff, nvalid, aligned, lim);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t c01[4], l01[4], c23[4], l23[4];
-    if (valid == 16) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j & 1)  // second quad of an eight-symbol group: no stray bits above its length
-          quad_code<true>(enc[byte_of(w[j], 0)], enc[byte_of(w[j], 1)], enc[byte_of(w[j], 2)], enc[byte_of(w[j], 3)],
-                          c01[j], l01[j], c23[j], l23[j]);
-        else
-          quad_code(enc[byte_of(w[j], 0)], enc[byte_of(w[j], 1)], enc[byte_of(w[j], 2)], enc[byte_of(w[j], 3)],
-                    c01[j], l01[j], c23[j], l23[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t e[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) e[i] = (uint32_t)(4 * j + i) < valid ? enc[byte_of(w[j], i)] : 0u;
-        quad_code<true>(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
-      }
-    }
+  auto entry = [&](uint32_t w, int i) { return lds_u32_ro(entry_addr(enc_addr, byte_of(w, i))); };
+  // 16 symbols per lane: entries -> quad codes -> two 64-bit puts at the lane's scanned position
+  auto encode16 = [&](const uint32_t (&c01)[4], const uint32_t (&l01)[4], const uint32_t (&c23)[4],
+                      const uint32_t (&l23)[4]) {
     uint32_t lq[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) lq[j] = l01[j] + l23[j];
@@ -480,6 +471,44 @@ __device__ inline unsigned long long encode_stream_staged_warp(const uint32_t* e
       }
     }
     bitpos += total;
+  };
+
+  // full groups of 512 symbols: every lane has 16, nothing to mask; the next group's symbols are
+  // requested one iteration ahead
+  const uint32_t full = sz >> 9;
+  uint32_t off = lane * 16;
+  uint4 vnext = make_uint4(0, 0, 0, 0);
+  if (full) vnext = load16(sp, off, 16, aligned, lim);
+  for (uint32_t it = 0; it < full; ++it) {
+    const uint4 v = vnext;
+    off += 512;
+    if (it + 1 < full) vnext = load16(sp, off, 16, aligned, lim);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t c01[4], l01[4], c23[4], l23[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j & 1)  // second quad of an eight-symbol group: no stray bits above its length
+        quad_code<true>(entry(w[j], 0), entry(w[j], 1), entry(w[j], 2), entry(w[j], 3), c01[j], l01[j], c23[j],
+                        l23[j]);
+      else
+        quad_code(entry(w[j], 0), entry(w[j], 1), entry(w[j], 2), entry(w[j], 3), c01[j], l01[j], c23[j], l23[j]);
+    }
+    encode16(c01, l01, c23, l23);
+  }
+  // the slice's last, partial group: symbols past its end contribute no bits
+  if (sz & 511u) {
+    const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
+    const uint4 v = load16(sp, off, valid, aligned, lim);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t c01[4], l01[4], c23[4], l23[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t e[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e[i] = (uint32_t)(4 * j + i) < valid ? entry(w[j], i) : 0u;
+      quad_code<true>(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
+    }
+    encode16(c01, l01, c23, l23);
   }
   __syncwarp();
   *overflow = over;
@@ -586,7 +615,7 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
       const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
       if (s < K) {
         geom(s, st, sz);
-        bits = encode_stream_staged_warp(tab.enc, stage_base, src + st, sz, &over, raw + n);
+        bits = encode_stream_staged_warp(smem_u32(tab.enc), stage_base, src + st, sz, &over, raw + n);
         if (bits > 12ull * sz) atomicOr(&sm.bad, 1u);  // a symbol without a code
         if (lane == 0) sm.stream_bits[s] = bits;
       }
@@ -670,6 +699,12 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
   }
 }
 
+// Work counters of the compress launches.  Every launch takes the next pair round-robin; a pair
+// is all-zero when idle (the last CTA of a launch re-arms it), and the ring is far longer than
+// the number of launches a device can have in flight.
+constexpr uint32_t kCounterSlots = 4096;
+__device__ uint32_t g_comp_counters[kCounterSlots][2];
+
 // Warp-specialised CTA: warps 0..7 are workers (histogram, encode), warp 8 builds tables.  While
 // the workers encode block b with table[cur], the builder turns the histogram of the CTA's next
 // block (counted by the workers just before) into table[cur^1]; its ~6k serial instructions
@@ -678,7 +713,8 @@ __global__ void __launch_bounds__(kCompThreads, kCompCtasPerSm)
 k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_size, int K,
                   uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
                   uint32_t* __restrict__ comp_sizes, const HufTable* __restrict__ shared_tab,
-                  int check_presence, uint32_t* __restrict__ status) {
+                  int check_presence, uint32_t* __restrict__ status, uint32_t counter_slot) {
+  uint32_t* const counters = g_comp_counters[counter_slot];  // [0] next block, [1] CTAs finished
   extern __shared__ __align__(1024) uint8_t comp_smem[];  // dynamic: the layout exceeds the 48 KiB static limit
   CompSmem& sm = *reinterpret_cast<CompSmem*>(comp_smem);
   if (smem_u32(comp_smem) & 1023u) __trap();  // ring_put/stage buffers rely on 1 KiB alignment
@@ -696,56 +732,80 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
   auto histogram_block = [&](uint32_t blk, int slot) {
     bins_accumulate(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
     worker_sync();
-    sm.hist[slot][tid] = bins_reduce_clear(sm.u.bins, tid);  // kWorkThreads == 256 bins
+    if (tid < 256) sm.hist[slot][tid] = bins_reduce_clear(sm.u.bins, tid);  // one thread per bin
   };
   auto build_table = [&](int slot) {
     if (block_size < (1u << 24)) build_table_warp<uint32_t, uint32_t>(sm.hist[slot], &sm.tab[slot], &sm.sc);
     else build_table_warp<uint32_t, unsigned long long>(sm.hist[slot], &sm.tab[slot], &sm.sc);
   };
 
-  if (blockIdx.x >= n_blocks) return;
   {  // the bins / staging union starts all-zero; every phase leaves it that way
     uint4* z = reinterpret_cast<uint4*>(&sm.u);
     for (int i = tid; i < (int)(sizeof(sm.u) / 16); i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
-  __syncthreads();
-  // ---- prologue: first block's histogram and table (or the shared table into both slots)
-  if (!builder && need_hist) histogram_block(blockIdx.x, 0);
-  if (!own_tables) {
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(shared_tab);
-    for (int t = 0; t < 2; ++t) {
-      uint32_t* d = reinterpret_cast<uint32_t*>(&sm.tab[t]);
-      for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += kCompThreads) d[i] = s[i];
-    }
+  // Blocks are handed out dynamically (one atomic per block on a per-launch counter): the CTAs
+  // that share an SM do not progress at the same rate, and with a static split the SM would
+  // run the last quarter of the kernel with one or two CTAs left.  A CTA always knows its
+  // current and its next block (the next one's histogram is pipelined).
+  if (tid == 0) {
+    sm.blk_new = atomicAdd(&counters[0], 1u);
+    sm.blk_new2 = atomicAdd(&counters[0], 1u);
   }
   __syncthreads();
-  if (builder && own_tables) build_table(0);
-  __syncthreads();
-
-  int cur = 0;
-  for (uint32_t b = blockIdx.x; b < n_blocks; b += gridDim.x) {
-    const uint32_t nb_next = b + gridDim.x;
-    const bool have_next = need_hist && nb_next < n_blocks;
-    // ---- phase A: the workers count the next block (the staging buffers of the previous block
-    //      are dead, the bins alias them); the builder has nothing to do yet
-    if (!builder) {
-      if (tid == 0) sm.bad = 0;
-      if (have_next) histogram_block(nb_next, cur ^ 1);
-    }
-    __syncthreads();
-    // ---- phase B: workers encode block b with table[cur] || builder makes table[cur^1]
-    if (builder) {
-      if (have_next && own_tables) build_table(cur ^ 1);
-    } else {
-      if (!own_tables && check_presence) {  // every symbol of the block needs a code in the supplied table
-        if (sm.hist[cur][tid] != 0 && sm.tab[cur].enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
+  uint32_t b = sm.blk_new, nxt = sm.blk_new2;
+  if (b < n_blocks) {
+    // ---- prologue: first block's histogram and table (or the shared table into both slots)
+    if (!builder && need_hist) histogram_block(b, 0);
+    if (!own_tables) {
+      const uint32_t* s = reinterpret_cast<const uint32_t*>(shared_tab);
+      for (int t = 0; t < 2; ++t) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(&sm.tab[t]);
+        for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += kCompThreads) d[i] = s[i];
       }
-      const uint64_t boff = (uint64_t)b * block_size;
-      encode_block_workers(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
-                           out + (uint64_t)b * slot_stride, comp_sizes + b, status);
     }
     __syncthreads();
-    cur ^= 1;
+    if (builder && own_tables) build_table(0);
+    __syncthreads();
+
+    int cur = 0;
+    while (b < n_blocks) {
+      const bool have_next = need_hist && nxt < n_blocks;
+      // ---- phase A: the workers count the next block (the staging buffers of the previous block
+      //      are dead, the bins alias them); the builder has nothing to do yet
+      if (!builder) {
+        if (tid == 0) {
+          sm.bad = 0;
+          sm.blk_new = atomicAdd(&counters[0], 1u);  // the block after the next one
+        }
+        if (have_next) histogram_block(nxt, cur ^ 1);
+      }
+      __syncthreads();
+      const uint32_t after_next = sm.blk_new;
+      // ---- phase B: workers encode block b with table[cur] || builder makes table[cur^1]
+      if (builder) {
+        if (have_next && own_tables) build_table(cur ^ 1);
+      } else {
+        if (!own_tables && check_presence) {  // every symbol of the block needs a code in the supplied table
+          if (tid < 256 && sm.hist[cur][tid] != 0 && sm.tab[cur].enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
+        }
+        const uint64_t boff = (uint64_t)b * block_size;
+        encode_block_workers(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
+                             out + (uint64_t)b * slot_stride, comp_sizes + b, status);
+      }
+      __syncthreads();
+      b = nxt;
+      nxt = after_next;
+      cur ^= 1;
+    }
+  }
+  // the last CTA to finish re-arms the counters for the next launch that uses this pair
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) {
+      counters[0] = 0;
+      counters[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -899,13 +959,6 @@ __device__ __forceinline__ void st_chunk32(uint8_t* addr, const uint32_t (&v)[8]
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
-// read-only data (the decode table inside the lookup loop): not volatile, no memory clobber, so
-// the compiler may schedule it across the loop's other shared-memory traffic
-__device__ __forceinline__ uint32_t lds_u32_ro(uint32_t addr) {
-  uint32_t v;
-  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -913,14 +966,6 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
-}
-
-// table base + 4 * index as one multiply-add: it runs on the FMA pipe, next to the lookup loop's
-// many ALU-pipe shifts and logic ops
-__device__ __forceinline__ uint32_t entry_addr(uint32_t base, uint32_t idx) {
-  uint32_t a;
-  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(idx), "r"(base));
-  return a;
 }
 
 // per-CTA scratch behind the tables: the T1 build scratch, later the lane rings and output rows
@@ -1259,6 +1304,8 @@ cudaError_t launch_make_table(const uint32_t* d_hist, const uint16_t* d_len_coun
   return cudaGetLastError();
 }
 
+static std::atomic<uint32_t> g_counter_slot{0};
+
 cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_size, int K, uint32_t n_blocks,
                             uint8_t* d_out, uint64_t slot_stride, uint32_t* d_sizes, const void* d_table,
                             int check_presence, uint32_t* d_status, int grid, cudaStream_t st) {
@@ -1275,7 +1322,8 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
   }
   k_compress_blocks<<<grid, kCompThreads, sizeof(CompSmem), st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride,
                                                    d_sizes, reinterpret_cast<const HufTable*>(d_table),
-                                                   check_presence, d_status);
+                                                   check_presence, d_status,
+                                                   g_counter_slot.fetch_add(1, std::memory_order_relaxed) % kCounterSlots);
   return cudaGetLastError();
 }
 

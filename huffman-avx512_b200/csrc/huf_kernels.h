@@ -12,7 +12,10 @@ constexpr int kHistThreads = 512;
 #ifndef HUF_COMP_MINB
 #define HUF_COMP_MINB 4
 #endif
-constexpr int kWorkThreads = 256;
+#ifndef HUF_COMP_WARPS
+#define HUF_COMP_WARPS 8
+#endif
+constexpr int kWorkThreads = 32 * HUF_COMP_WARPS;  // >= 256: one thread per bin in the reduction
 constexpr int kCompThreads = kWorkThreads + 32;
 constexpr int kCompCtasPerSm = HUF_COMP_MINB;
 constexpr int kCompWarps = kWorkThreads / 32;  // worker warps
