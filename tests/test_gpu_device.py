@@ -97,3 +97,49 @@ def test_full_size_roundtrip_properties(huf, oracle):
         b = int(b)
         blk = slots[b * codec.slot_stride: b * codec.slot_stride + int(sz[b])].cpu().numpy().tobytes()
         assert blk == oracle.compress(k, raw[b * bs: (b + 1) * bs].cpu().numpy().tobytes()), b
+
+
+def test_concurrent_launches_on_two_streams(huf, oracle):
+    """Compress launches hand their blocks out through per-launch work counters: launches that
+    overlap on different streams must not disturb each other."""
+    import torch
+    k, bs = 32, 16384
+    nblk = 96
+    datas = [biased(nblk * bs, seed=100 + i) for i in range(2)]
+    codec = huf.BlockCodec(k, bs)
+    raws = [_t(d) for d in datas]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = [codec.alloc_slots(nblk * bs) for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(8):
+        for i, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                codec.compress(raws[i], slots=outs[i][0], sizes=outs[i][1])
+    torch.cuda.synchronize()
+    for i in range(2):
+        sz = outs[i][1].cpu().numpy()
+        sl = outs[i][0].cpu().numpy()
+        for b in (0, 1, nblk // 2, nblk - 1):
+            blk = sl[b * codec.slot_stride: b * codec.slot_stride + sz[b]].tobytes()
+            assert blk == oracle.compress(k, datas[i][b * bs: (b + 1) * bs]), (i, b)
+        out = codec.decompress(outs[i][0], codec.slot_offsets(nblk * bs), outs[i][1], nblk * bs)
+        assert out[: nblk * bs].cpu().numpy().tobytes() == datas[i]
+
+
+def test_many_launches_wrap_the_counter_ring(huf, oracle):
+    """More launches than the ring of work counters has entries (4096): every pair must come back
+    armed."""
+    import torch
+    k, bs = 8, 4096
+    data = biased(3 * bs + 100, seed=7)
+    codec = huf.BlockCodec(k, bs)
+    raw = _t(data)
+    slots, sizes = codec.alloc_slots(len(data))
+    for _ in range(4500):
+        codec.compress(raw, slots=slots, sizes=sizes)
+    torch.cuda.synchronize()
+    sz = sizes.cpu().numpy()
+    sl = slots.cpu().numpy()
+    for b in range(codec.n_blocks(len(data))):
+        blk = sl[b * codec.slot_stride: b * codec.slot_stride + sz[b]].tobytes()
+        assert blk == oracle.compress(k, data[b * bs: (b + 1) * bs]), b
