@@ -71,8 +71,20 @@ __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p
   const uint64_t nvec = (n - head) >> 4;
   uint64_t i = t;
   const uint64_t step = nt;
-  for (; i + 3 * step < nvec; i += 4 * step) {  // 4 loads in flight per thread
-    const uint4 a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
+  if (i + 3 * step < nvec) {  // batches of 4 loads per thread, the next batch in flight while one is counted
+    uint4 a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
+    i += 4 * step;
+    for (; i + 3 * step < nvec; i += 4 * step) {
+      const uint4 a2 = v[i], b2 = v[i + step], c2 = v[i + 2 * step], d2 = v[i + 3 * step];
+      bins_add_vec(bl, a);
+      bins_add_vec(bl, b);
+      bins_add_vec(bl, c);
+      bins_add_vec(bl, d);
+      a = a2;
+      b = b2;
+      c = c2;
+      d = d2;
+    }
     bins_add_vec(bl, a);
     bins_add_vec(bl, b);
     bins_add_vec(bl, c);
