@@ -487,14 +487,18 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
 
   // full groups of 512 symbols: every lane has 16, nothing to mask; the next group's symbols are
   // requested one iteration ahead
-  const uint32_t full = sz >> 9;
+  uint32_t groups = sz >> 9;  // full groups still to do
+  // keep the trip count and the two shared-memory bases in registers: under the kernel's register
+  // cap the compiler would otherwise re-derive them from the slice geometry and %warpid every trip
+  asm volatile("" : "+r"(groups), "+r"(stage_base), "+r"(enc_addr));
   uint32_t off = lane * 16;
   uint4 vnext = make_uint4(0, 0, 0, 0);
-  if (full) vnext = load16(sp, off, 16, aligned, lim);
-  for (uint32_t it = 0; it < full; ++it) {
+  if (groups) vnext = load16(sp, off, 16, aligned, lim);
+  while (groups) {
     const uint4 v = vnext;
     off += 512;
-    if (it + 1 < full) vnext = load16(sp, off, 16, aligned, lim);
+    --groups;
+    if (groups) vnext = load16(sp, off, 16, aligned, lim);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t c01[4], l01[4], c23[4], l23[4];
 #pragma unroll
