@@ -166,6 +166,7 @@ constexpr int kRingWords = 256;  // per-warp staging ring, in 32-bit stream word
 // stream in shared memory, so the stream's size is known without a separate length pass.
 constexpr int kStageSlice = 4096;
 constexpr int kStageWords = 1280;  // 5 KiB per warp = 10 bits/symbol; longer streams take the ring path
+constexpr int kStageFront = 2;     // spare words before stream word 0 (see stage_put64_end)
 
 struct CompSmem {
   union {
@@ -329,6 +330,18 @@ __device__ __forceinline__ void stage_put64(uint32_t stage_base, uint32_t pos, u
   red_or_shared(a0 + 8u, shl_c(lo, 32u - o));
 }
 
+// Up to 64 bits whose LAST bit sits just before stream bit position `end`: the value is taken
+// right-aligned (bits above its length must be zero), so nothing has to be left-aligned first:
+// with r = end % 32 the three words ending at word end/32 are hi >> r, (hi:lo) >> r and
+// lo << (32 - r).  Words that get nothing receive an OR with 0 (hence two spare words in front
+// of the stream, kStageFront).
+__device__ __forceinline__ void stage_put64_end(uint32_t stream_base, uint32_t end, uint32_t hi, uint32_t lo) {
+  const uint32_t a = entry_addr(stream_base, end >> 5);
+  red_or_shared(a - 8u, __funnelshift_r(hi, 0u, end));  // hi >> r
+  red_or_shared(a - 4u, __funnelshift_r(lo, hi, end));  // shift amount = end & 31
+  red_or_shared(a, __funnelshift_r(0u, lo, end));       // lo << (32 - r), 0 for r == 0
+}
+
 // Four table entries (first symbol first) -> the two pair codes and lengths.  c01 may carry
 // garbage above l01 bits (it always ends up left-aligned by a shift); c23 is clean.
 template <bool CLEAN = false>
@@ -447,6 +460,7 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
   uint32_t bitpos = 0;  // a staged stream is at most kStageSlice * 12 bits long
   bool over = false;
+  uint32_t sb = stage_base + 4u * kStageFront;  // stream word 0
   auto entry = [&](uint32_t w, int i) { return lds_u32_ro(entry_addr(enc_addr, byte_of(w, i))); };
   // 16 symbols per lane: entries -> quad codes -> two 64-bit puts at the lane's scanned position
   auto encode16 = [&](const uint32_t (&c01)[4], const uint32_t (&l01)[4], const uint32_t (&c23)[4],
@@ -458,7 +472,7 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
     const uint32_t incl = warp_incl_scan(lane_len);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     // a symbol without a code makes `total` huge and lands here as an overflow, too
-    if (bitpos + total > (uint32_t)(kStageWords - 2) * 32) over = true;  // puts touch up to 3 words
+    if (bitpos + total > (uint32_t)(kStageWords - kStageFront - 2) * 32) over = true;  // puts touch up to 3 words
     if (!over) {
       uint32_t pos = bitpos + (incl - lane_len);
 #pragma unroll
@@ -466,16 +480,16 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
         if (lq[h] <= 32 && lq[h + 1] <= 32) {  // almost always: one put for eight symbols
           const uint32_t qa = (c01[h] << l23[h]) | c23[h];
           const uint32_t qb = (c01[h + 1] << l23[h + 1]) | c23[h + 1];
-          stage_put64(stage_base, pos, ((unsigned long long)qa << lq[h + 1]) | qb, lq[h] + lq[h + 1]);
           pos += lq[h] + lq[h + 1];
+          stage_put64_end(sb, pos, __funnelshift_lc(qa, 0u, lq[h + 1]), shl_c(qa, lq[h + 1]) | qb);
         } else {
 #pragma unroll
           for (int j = h; j < h + 2; ++j) {
             if (lq[j] <= 32) {
-              stage_put(stage_base, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
+              stage_put(sb, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
             } else {
-              stage_put(stage_base, pos, c01[j], l01[j]);
-              stage_put(stage_base, pos + l01[j], c23[j], l23[j]);
+              stage_put(sb, pos, c01[j], l01[j]);
+              stage_put(sb, pos + l01[j], c23[j], l23[j]);
             }
             pos += lq[j];
           }
@@ -486,31 +500,34 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   };
 
   // full groups of 512 symbols: every lane has 16, nothing to mask; the next group's symbols are
-  // requested one iteration ahead
+  // requested one iteration ahead.  The loop exists twice: slices that start on a 16-byte
+  // boundary (all shapes where K divides the block nicely) take plain 128-bit loads.
   uint32_t groups = sz >> 9;  // full groups still to do
-  // keep the trip count and the two shared-memory bases in registers: under the kernel's register
+  // keep the trip count and the shared-memory bases in registers: under the kernel's register
   // cap the compiler would otherwise re-derive them from the slice geometry and %warpid every trip
-  asm volatile("" : "+r"(groups), "+r"(stage_base), "+r"(enc_addr));
-  uint32_t off = lane * 16;
-  uint4 vnext = make_uint4(0, 0, 0, 0);
-  if (groups) vnext = load16(sp, off, 16, aligned, lim);
-  while (groups) {
-    const uint4 v = vnext;
-    off += 512;
-    --groups;
-    if (groups) vnext = load16(sp, off, 16, aligned, lim);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t c01[4], l01[4], c23[4], l23[4];
+  asm volatile("" : "+r"(groups), "+r"(sb), "+r"(enc_addr));
+  const uint32_t off = lane * 16 + ((sz >> 9) << 9);  // this lane's symbols of the partial last group
+  auto full_groups = [&](auto aligned_tag) {
+    constexpr bool kAligned = decltype(aligned_tag)::value;
+    const uint8_t* p = sp + lane * 16;  // this lane's 16 symbols of the next group
+    uint4 vnext = make_uint4(0, 0, 0, 0);
+    if (groups) vnext = kAligned ? *reinterpret_cast<const uint4*>(p) : load16(p, 0, 16, false, lim);
+    while (groups) {
+      const uint4 v = vnext;
+      p += 512;
+      --groups;
+      if (groups) vnext = kAligned ? *reinterpret_cast<const uint4*>(p) : load16(p, 0, 16, false, lim);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t c01[4], l01[4], c23[4], l23[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j & 1)  // second quad of an eight-symbol group: no stray bits above its length
+      for (int j = 0; j < 4; ++j)
         quad_code<true>(entry(w[j], 0), entry(w[j], 1), entry(w[j], 2), entry(w[j], 3), c01[j], l01[j], c23[j],
                         l23[j]);
-      else
-        quad_code(entry(w[j], 0), entry(w[j], 1), entry(w[j], 2), entry(w[j], 3), c01[j], l01[j], c23[j], l23[j]);
+      encode16(c01, l01, c23, l23);
     }
-    encode16(c01, l01, c23, l23);
-  }
+  };
+  if (aligned) full_groups(std::true_type{});
+  else full_groups(std::false_type{});
   // the slice's last, partial group: symbols past its end contribute no bits
   if (sz & 511u) {
     const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
@@ -543,7 +560,7 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
   const uint32_t m_last = (e_al - s_al) >> 2;  // inclusive
   const uint32_t wtot = (uint32_t)((bits + 31) >> 5);
   uint32_t* out = reinterpret_cast<uint32_t*>(dst + e_al) - lane;  // this lane's word of the current row
-  uint32_t sa = stage_base + 4u * (uint32_t)lane;
+  uint32_t sa = stage_base + 4u * (uint32_t)(kStageFront + lane);  // stream word `lane`
   uint32_t carry = 0;
   uint32_t m0 = 0;
   // full rows: 32 data words each, no predicates
