@@ -112,7 +112,9 @@ HUFB200_API int hufb200_compress_blocks_dev(int k, size_t block_size, const uint
                                 const void* d_table, uint32_t* d_status, void* stream);
 /* Decodes n_blocks blocks; block b starts at d_comp + d_offsets[b], is d_comp_sizes[b] bytes long
  * and decodes to d_raw + b*block_size (raw_n total bytes; the last block may be shorter).  The
- * allocation behind d_comp must extend to the next 32-byte boundary after the last block. */
+ * compressed bytes are fetched in whole aligned 32-byte sectors: the allocation that holds d_comp
+ * must cover the sectors of its first and last byte (true for any pointer into cudaMalloc'ed
+ * memory whose allocation extends to the next 32-byte boundary after the last block). */
 HUFB200_API int hufb200_decompress_blocks_dev(int k, size_t block_size, const uint8_t* d_comp,
                                   const uint64_t* d_offsets, const uint32_t* d_comp_sizes,
                                   size_t n_blocks, uint8_t* d_raw, size_t raw_n,
