@@ -473,27 +473,28 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     // a symbol without a code makes `total` huge and lands here as an overflow, too
     if (bitpos + total > (uint32_t)(kStageWords - kStageFront - 2) * 32) over = true;  // puts touch up to 3 words
-    if (!over) {
-      uint32_t pos = bitpos + (incl - lane_len);
+    // one decision per lane and trip: all four quads at most 32 bits long (practically always)
+    // -> two 64-bit puts; else the quads one by one
+    const uint32_t longest = max(max(lq[0], lq[1]), max(lq[2], lq[3]));
+    uint32_t pos = bitpos + (incl - lane_len);
+    if (!over && longest <= 32u) {
 #pragma unroll
       for (int h = 0; h < 4; h += 2) {
-        if (lq[h] <= 32 && lq[h + 1] <= 32) {  // almost always: one put for eight symbols
-          const uint32_t qa = (c01[h] << l23[h]) | c23[h];
-          const uint32_t qb = (c01[h + 1] << l23[h + 1]) | c23[h + 1];
-          pos += lq[h] + lq[h + 1];
-          stage_put64_end(sb, pos, __funnelshift_lc(qa, 0u, lq[h + 1]), shl_c(qa, lq[h + 1]) | qb);
-        } else {
+        const uint32_t qa = (c01[h] << l23[h]) | c23[h];
+        const uint32_t qb = (c01[h + 1] << l23[h + 1]) | c23[h + 1];
+        pos += lq[h] + lq[h + 1];
+        stage_put64_end(sb, pos, __funnelshift_lc(qa, 0u, lq[h + 1]), shl_c(qa, lq[h + 1]) | qb);
+      }
+    } else if (!over) {
 #pragma unroll
-          for (int j = h; j < h + 2; ++j) {
-            if (lq[j] <= 32) {
-              stage_put(sb, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
-            } else {
-              stage_put(sb, pos, c01[j], l01[j]);
-              stage_put(sb, pos + l01[j], c23[j], l23[j]);
-            }
-            pos += lq[j];
-          }
+      for (int j = 0; j < 4; ++j) {
+        if (lq[j] <= 32) {
+          stage_put(sb, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
+        } else {
+          stage_put(sb, pos, c01[j], l01[j]);
+          stage_put(sb, pos + l01[j], c23[j], l23[j]);
         }
+        pos += lq[j];
       }
     }
     bitpos += total;
