@@ -106,7 +106,9 @@ HUFB200_API size_t hufb200_slot_stride(size_t block_size, int k);
  * to d_comp_sizes[b].  Up to 3 zero bytes may be written past a block's end inside its slot.
  * d_table: NULL = one table per block (the reference's behaviour); otherwise a shared table
  * built by hufb200_build_table_dev (every block still carries the full header).
- * d_status: one u32, set non-zero by the kernel on E_CORRUPT conditions (may be NULL). */
+ * d_status: one u32, set non-zero by the kernel on E_CORRUPT conditions (may be NULL).
+ * Launches may overlap on different streams; each takes one of 4096 device-side work counters in
+ * turn, so at most 4095 compress launches may be outstanding on a device at once. */
 HUFB200_API int hufb200_compress_blocks_dev(int k, size_t block_size, const uint8_t* d_raw, size_t n,
                                 uint8_t* d_out, size_t slot_stride, uint32_t* d_comp_sizes,
                                 const void* d_table, uint32_t* d_status, void* stream);
