@@ -1130,11 +1130,16 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // whose byte positions are congruent to the output addresses mod 16, so every complete 16-byte
   // ring chunk leaves as one aligned 128-bit store.  acc: bits 0..5 = bits consumed from the
   // window, bits 6.. = ring write position in bytes (starts at the slice's misalignment h0).
-  const uint32_t h0 = (uint32_t)((uintptr_t)outp & (kDecChunk - 1));
-  uint8_t* const out_al = outp - h0;                   // chunk-aligned; ring byte p <-> out_al[p]
-  const uint32_t end_pos = h0 + left;                   // ring position one past the last symbol
-  const uint32_t end_acc = end_pos << 6;
-  const uint32_t full_chunks = end_pos >> 5;            // chunks that lie entirely inside the slice
+  // Positions live in bits 6..31 of acc, so they are kept below 2^26: a stream longer than
+  // kPosWindow symbols is decoded through a window of positions that is moved along (see the
+  // rebase at the top of the round loop); `beyond` = symbols past the window's end.
+  constexpr uint32_t kPosWindow = 1u << 25;
+  uint32_t beyond = left > kPosWindow ? left - kPosWindow : 0u;
+  uint32_t h0 = (uint32_t)((uintptr_t)outp & (kDecChunk - 1));
+  uint8_t* out_al = outp - h0;                           // chunk-aligned; ring byte p <-> out_al[p]
+  uint32_t end_pos = h0 + (left - beyond);               // ring position one past the last symbol (of the window)
+  uint32_t end_acc = end_pos << 6;
+  uint32_t full_chunks = end_pos >> 5;                   // chunks that lie entirely inside the slice
   acc |= h0 << 6;
   uint32_t wofs = (h0 >> 2) * 128;                      // byte offset of the ring word being filled
   uint32_t chunk = 0;                                   // next 32-byte chunk to write out
@@ -1173,9 +1178,28 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   };
   // a lane is "far" from its end if a whole round cannot exhaust it; lanes without a stream run
   // harmless lookups on a zero window in unchecked rounds (private rings, nothing is emitted)
-  const uint32_t far_acc = end_acc >= ((3u * kDecLookups) << 6) ? end_acc - ((3u * kDecLookups) << 6) : 0u;
+  uint32_t far_acc = end_acc >= ((3u * kDecLookups) << 6) ? end_acc - ((3u * kDecLookups) << 6) : 0u;
   const bool no_stream = !active || left == 0;
+  const bool long_streams = __any_sync(0xffffffffu, left >= kPosWindow / 2 - 64);  // can a position reach the rebase point?
   while (__any_sync(0xffffffffu, acc < end_acc)) {
+    // rare (streams of more than 16 Mi symbols): move the position window.  Everything already
+    // written out is dropped from the positions -- a multiple of the 64-byte ring, so ring
+    // offsets keep their meaning -- and the window's end moves on by as much as is left.
+    if (long_streams) {
+      if (acc >= ((kPosWindow / 2) << 6)) {
+        const uint32_t delta = (chunk & ~(uint32_t)(kDecRow / kDecChunk - 1)) * (uint32_t)kDecChunk;
+        const uint32_t add = beyond < delta ? beyond : delta;
+        beyond -= add;
+        acc -= delta << 6;
+        chunk -= delta / (uint32_t)kDecChunk;
+        out_al += delta;
+        h0 = 0;  // the slice's head lies behind
+        end_pos = end_pos - delta + add;
+        end_acc = end_pos << 6;
+        full_chunks = end_pos >> 5;
+        far_acc = end_acc >= ((3u * kDecLookups) << 6) ? end_acc - ((3u * kDecLookups) << 6) : 0u;
+      }
+    }
     // Top up the input ring: a round consumes at most 5 words (+1 looked ahead).  The sector
     // stored now was requested at the previous top-up, so its latency is hidden.
     if (staged - rd <= 8) {  // room for a sector; afterwards at least 9 words are staged

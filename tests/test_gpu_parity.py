@@ -232,3 +232,15 @@ def test_decoder_survives_corrupt_input(huf):
         except huf.HufError as e:
             assert e.code in (-1, -2, -4)
     assert huf.decompress_blocks(bytes(cont)) == good_data
+
+
+def test_stream_longer_than_the_position_window(huf, oracle):
+    """One stream of more than 2^26 symbols: the decoder keeps positions in 26 bits and has to
+    move its window along (found by a 70 MiB single-stream round trip)."""
+    from _cases import biased
+    n = (65 << 20) + 4321
+    blk = biased(1 << 20, seed=5)
+    data = (blk * ((n >> 20) + 1))[:n]
+    comp = huf.compress(1, data)
+    assert comp == oracle.compress(1, data)
+    assert huf.decompress(1, comp) == data
