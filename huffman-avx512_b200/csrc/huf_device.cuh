@@ -191,6 +191,106 @@ __device__ inline void partition_phase(K* a, int n, int32_t* st_first, int32_t* 
     depth = st_depth[sp];
   }
 }
+
+// The same loop run by the whole warp.  What one __unguarded_partition call does to its range is
+// fixed by two lists taken from the range as it is before the call: A = positions (ascending)
+// whose key does not sort before the pivot -- where the left scan stops -- and B = positions
+// (descending) whose key does not sort after it -- where the right scan stops.  The i-th
+// iteration swaps a[A_i] and a[B_i] as long as A_i < B_i (a swapped element lands behind the
+// scan pointers, so the lists never need updating), and the left scan that ends the loop stops
+// at the next A position or at B_s, which holds an A-type element after the last swap.  So the
+// lists are built with ballots, all swaps happen at once, and the cut is min(A_{s+1}, B_s).
+// The heapsort fallback stays serial (lane 0).  listA / listB: 256 entries each.
+template <typename K>
+__device__ inline void partition_phase_warp(K* a, int n, int32_t* st_first, int32_t* st_last, int32_t* st_depth,
+                                            uint16_t* listA, uint16_t* listB) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int sp = 0;
+  int first = 0, last = n, depth = 2 * (31 - __clz(n));
+  for (;;) {
+    while (last - first > 16) {
+      if (depth == 0) {
+        if (lane == 0) heap_sort(a, first, last);
+        __syncwarp();
+        break;
+      }
+      --depth;
+      const int mid = first + (last - first) / 2;
+      K pivot;
+      {  // __move_median_to_first(first, first+1, mid, last-1); every lane reads the same words
+        const K ka = a[first + 1], kb = a[mid], kc = a[last - 1];
+        int pick;
+        if (less(ka, kb)) {
+          if (less(kb, kc)) pick = mid;
+          else if (less(ka, kc)) pick = last - 1;
+          else pick = first + 1;
+        } else if (less(ka, kc)) pick = first + 1;
+        else if (less(kb, kc)) pick = last - 1;
+        else pick = mid;
+        pivot = a[pick];
+        const K old_first = a[first];
+        __syncwarp();
+        if (lane == 0) {
+          a[pick] = old_first;
+          a[first] = pivot;
+        }
+        __syncwarp();
+      }
+      // the two stop lists over [first+1, last)
+      int nA = 0, nB = 0;
+      for (int base = first + 1; base < last; base += 32) {
+        const int p = base + lane;
+        const bool f = p < last && !less(a[p < last ? p : first], pivot);
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (f) listA[nA + __popc(m & lt)] = (uint16_t)p;
+        nA += __popc(m);
+      }
+      for (int top = last - 1; top > first; top -= 32) {
+        const int p = top - lane;
+        const bool f = p > first && !less(pivot, a[p > first ? p : first]);
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (f) listB[nB + __popc(m & lt)] = (uint16_t)p;
+        nB += __popc(m);
+      }
+      __syncwarp();
+      // s = number of swaps; A ascends and B descends, so the valid pairs are a prefix
+      const int nm = nA < nB ? nA : nB;
+      int s = 0;
+      for (int i0 = 0; i0 < nm; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned m = __ballot_sync(0xffffffffu, i < nm && listA[i < nm ? i : 0] < listB[i < nm ? i : 0]);
+        s += __popc(m);
+        if (m != 0xffffffffu) break;
+      }
+      for (int i = lane; i < s; i += 32) {
+        const int pa = listA[i], pb = listB[i];
+        const K t = a[pa];
+        a[pa] = a[pb];
+        a[pb] = t;
+      }
+      int cut;
+      if (s == 0) cut = listA[0];  // the median move guarantees nA >= 1 and nB >= 1
+      else {
+        cut = listB[s - 1];
+        if (s < nA && (int)listA[s] < cut) cut = listA[s];
+      }
+      __syncwarp();
+      st_first[sp] = cut;  // right part [cut, last) for later, left part [first, cut) now (same value from every lane)
+      st_last[sp] = last;
+      st_depth[sp] = depth;
+      ++sp;
+      last = cut;
+    }
+    if (sp == 0) break;
+    --sp;
+    __syncwarp();
+    first = st_first[sp];
+    last = st_last[sp];
+    depth = st_depth[sp];
+  }
+  __syncwarp();
+}
 }  // namespace sortclone
 
 // ---------------------------------------------------------------------------
@@ -227,21 +327,25 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
   __syncwarp();
 
   if (n > 0) {
-    // 2a. introsort partition phase (serial, only for n > 16)
-    if (n > 16) {
-      if (lane == 0) sortclone::partition_phase(keys, n, sc->st_first, sc->st_last, sc->st_depth);
-      __syncwarp();
-    }
-    // 2b. final insertion sort == stable sort: rank = #greater + #equal-before
+    // 2a. introsort partition phase (only for n > 16); it leaves runs of at most 16 elements (or
+    //     heap-sorted ranges) that are in order among each other
+    if (n > 16) sortclone::partition_phase_warp(keys, n, sc->st_first, sc->st_last, sc->st_depth, sc->par[0], sc->par[1]);
+    // 2b. final insertion sort == stable sort of what 2a left: rank = #greater + #equal-before.
+    //     No element moves out of its run, so only the 16 neighbours on either side can change
+    //     places with it; everything further left ranks before it, everything further right after.
     for (int i0 = 0; i0 < n; i0 += 32) {
       const int i = i0 + lane;
       const KeyT mine = i < n ? keys[i] : 0;
       const KeyT mc = mine >> 8;
-      int rank = 0;
-#pragma unroll 4
-      for (int j = 0; j < n; ++j) {
-        const KeyT oc = keys[j] >> 8;  // broadcast read
-        rank += ((oc > mc) || (oc == mc && j < i)) ? 1 : 0;
+      const int w0 = i - 16;
+      int rank = w0 > 0 ? w0 : 0;
+#pragma unroll 3
+      for (int t = 0; t < 33; ++t) {
+        const int j = w0 + t;
+        if (j >= 0 && j < n) {
+          const KeyT oc = keys[j] >> 8;
+          rank += ((oc > mc) || (oc == mc && j < i)) ? 1 : 0;
+        }
       }
       if (i < n) sorted[rank] = mine;
     }
@@ -287,13 +391,17 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
       int cur = 0;
 #pragma unroll 1
       for (int round = 0; round < 8; ++round) {
+        bool open = false;  // some link of this lane does not point at the root yet
         for (int i = lane; i < n_nodes; i += 32) {
           const int p = sc->par[cur][i];
+          const int pp = sc->par[cur][p];
           sc->dep[cur ^ 1][i] = sc->dep[cur][i] + sc->dep[cur][p];
-          sc->par[cur ^ 1][i] = sc->par[cur][p];
+          sc->par[cur ^ 1][i] = (uint16_t)pp;
+          open |= pp != n_nodes - 1;
         }
         cur ^= 1;
         __syncwarp();
+        if (!__any_sync(0xffffffffu, open)) break;  // every node has its full depth
       }
       for (int i = lane; i < n; i += 32) {
         const int d = sc->dep[cur][sc->leaf_parent[i]] + 1;

@@ -244,3 +244,40 @@ def test_stream_longer_than_the_position_window(huf, oracle):
     comp = huf.compress(1, data)
     assert comp == oracle.compress(1, data)
     assert huf.decompress(1, comp) == data
+
+
+def test_table_build_sort_order_stress(huf, oracle):
+    """The warp-parallel restatement of libstdc++'s introsort partition phase against the oracle:
+    tie-heavy random histograms and orders that force deep recursion / the heapsort fallback."""
+    rng = np.random.default_rng(11)
+    hists = []
+    for trial in range(400):
+        n = int(rng.integers(1, 257))
+        hi = int(rng.choice([1, 2, 3, 5, 20, 1000]))
+        h = np.zeros(256, dtype=np.uint32)
+        h[rng.permutation(256)[:n]] = rng.integers(1, hi + 1, n)
+        hists.append(h)
+    for n in (64, 128, 200, 256):
+        for pattern in range(4):
+            h = np.zeros(256, dtype=np.uint32)
+            idx = np.arange(n)
+            if pattern == 0:
+                vals = np.where(idx % 2 == 0, idx + 1, n + idx)
+            elif pattern == 1:
+                vals = np.concatenate([np.arange(1, n // 2 + 1), np.arange(n // 2, 0, -1)])[:n]
+            elif pattern == 2:
+                vals = (idx * 7919) % 13 + 1
+            else:  # median-of-3 killer
+                vals = np.zeros(n, dtype=np.int64)
+                half = n // 2
+                for i in range(half):
+                    vals[i] = i + 1 if i % 2 == 0 else half + i + (1 if i % 2 else 0)
+                    vals[half + i] = 2 * (i + 1)
+            h[:n] = vals[:n]
+            hists.append(h)
+    for t, h in enumerate(hists):
+        want = oracle.make_coding(h)
+        got = huf.make_table(h)
+        assert got["sorted_syms"] == want["sorted_syms"], t
+        assert np.array_equal(got["len_count"], want["len_count"]), t
+        assert np.array_equal(got["code_bits"], want["code_bits"]), t
