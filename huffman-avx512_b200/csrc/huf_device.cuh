@@ -139,60 +139,9 @@ __device__ inline void heap_sort(K* a, int first, int last) {
   }
 }
 
-// std::__introsort_loop on a[0..n), n > 16: ONE thread.  The recursion on the right part is an
-// explicit stack; the two parts are disjoint so their processing order does not matter.
-template <typename K>
-__device__ inline void partition_phase(K* a, int n, int32_t* st_first, int32_t* st_last, int32_t* st_depth) {
-  int sp = 0;
-  int first = 0, last = n, depth = 2 * (31 - __clz(n));
-  for (;;) {
-    while (last - first > 16) {
-      if (depth == 0) {
-        heap_sort(a, first, last);
-        break;
-      }
-      --depth;
-      const int mid = first + (last - first) / 2;
-      {  // __move_median_to_first(first, first+1, mid, last-1)
-        const K ka = a[first + 1], kb = a[mid], kc = a[last - 1];
-        int pick;
-        if (less(ka, kb)) {
-          if (less(kb, kc)) pick = mid;
-          else if (less(ka, kc)) pick = last - 1;
-          else pick = first + 1;
-        } else if (less(ka, kc)) pick = first + 1;
-        else if (less(kb, kc)) pick = last - 1;
-        else pick = mid;
-        swp(a, first, pick);
-      }
-      // __unguarded_partition(first+1, last, pivot = *first)
-      const K pivot = a[first];
-      int lo = first + 1, hi = last;
-      for (;;) {
-        K kl = a[lo];
-        while (less(kl, pivot)) kl = a[++lo];
-        K kh = a[--hi];
-        while (less(pivot, kh)) kh = a[--hi];
-        if (!(lo < hi)) break;
-        a[lo] = kh;
-        a[hi] = kl;
-        ++lo;
-      }
-      st_first[sp] = lo;  // right part [cut, last) for later, left part [first, cut) now
-      st_last[sp] = last;
-      st_depth[sp] = depth;
-      ++sp;
-      last = lo;
-    }
-    if (sp == 0) break;
-    --sp;
-    first = st_first[sp];
-    last = st_last[sp];
-    depth = st_depth[sp];
-  }
-}
-
-// The same loop run by the whole warp.  What one __unguarded_partition call does to its range is
+// std::__introsort_loop on a[0..n), n > 16 (the recursion on the right part is an explicit stack;
+// the two parts are disjoint so their processing order does not matter), run by the whole warp.
+// What one __unguarded_partition call does to its range is
 // fixed by two lists taken from the range as it is before the call: A = positions (ascending)
 // whose key does not sort before the pivot -- where the left scan stops -- and B = positions
 // (descending) whose key does not sort after it -- where the right scan stops.  The i-th
@@ -339,13 +288,15 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
       const KeyT mc = mine >> 8;
       const int w0 = i - 16;
       int rank = w0 > 0 ? w0 : 0;
-#pragma unroll 3
+      // straight-line: 33 independent loads (index clamped into the array, the in-range test
+      // decides whether the comparison counts)
+#pragma unroll
       for (int t = 0; t < 33; ++t) {
         const int j = w0 + t;
-        if (j >= 0 && j < n) {
-          const KeyT oc = keys[j] >> 8;
-          rank += ((oc > mc) || (oc == mc && j < i)) ? 1 : 0;
-        }
+        const int jc = j < 0 ? 0 : (j < n ? j : n - 1);
+        const KeyT oc = keys[jc] >> 8;
+        const bool before = (oc > mc) || (oc == mc && t < 16);  // t < 16 <=> j < i
+        rank += ((unsigned)j < (unsigned)n && before) ? 1 : 0;
       }
       if (i < n) sorted[rank] = mine;
     }
@@ -411,27 +362,40 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
       sc->len_count33[0] = 1;  // one symbol: the root is a leaf at depth 0 (:417-418)
     }
     __syncwarp();
-    // 5. LimitCodeLengths (:297-327), serial and tiny
-    if (lane == 0) {
+    // 5. LimitCodeLengths (:297-327): lane l holds len_count[l] (l <= 12; deeper levels folded
+    //    into 12 first), the Kraft sum is a warp reduction, and each repair step -- one leaf off
+    //    level 12, the deepest non-empty shallower level j gives one to j+1 twice -- is a ballot
+    //    and three predicated register updates instead of a walk over shared memory
+    {
       uint32_t* lc = sc->len_count33;
-      for (int i = kMaxCodeLen + 1; i <= 32; ++i) {
-        lc[kMaxCodeLen] += lc[i];
-        lc[i] = 0;
-      }
-      uint32_t kraft = 0;
-      for (int i = 0; i <= kMaxCodeLen; ++i) kraft += lc[i] << (kMaxCodeLen - i);
+      uint32_t mine = lane <= 32 ? lc[lane] : 0u;  // lane 32 does not exist: levels 0..31 here, level 32 below
+      uint32_t deep = (lane > kMaxCodeLen) ? mine : 0u;
+      if (lane == 0) deep += lc[32];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) deep += __shfl_xor_sync(0xffffffffu, deep, d);
+      if (lane == kMaxCodeLen) mine += deep;
+      if (lane > kMaxCodeLen) mine = 0;
+      uint32_t kraft = lane <= kMaxCodeLen ? (mine << (kMaxCodeLen - lane)) : 0u;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) kraft += __shfl_xor_sync(0xffffffffu, kraft, d);
       const uint32_t one = 1u << kMaxCodeLen;
       while (kraft > one) {
-        --lc[kMaxCodeLen];
-        for (int j = kMaxCodeLen - 1; j >= 0; --j) {
-          if (lc[j] > 0) {
-            --lc[j];
-            lc[j + 1] += 2;
-            break;
-          }
+        if (lane == kMaxCodeLen) --mine;
+        const unsigned nonempty = __ballot_sync(0xffffffffu, lane < kMaxCodeLen && mine > 0);
+        if (nonempty) {
+          const int j = 31 - __clz(nonempty);
+          if (lane == j) --mine;
+          if (lane == j + 1) mine += 2;
         }
         --kraft;
       }
+      if (lane <= kMaxCodeLen) lc[lane] = mine;
+      else if (lane < 32) lc[lane] = 0;
+      if (lane == 0) lc[32] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t* lc = sc->len_count33;
       // prefix tables for the canonical assignment
       uint32_t cum = 0, code = 0, mask = 0;
       for (int l = 0; l <= kMaxCodeLen; ++l) {
