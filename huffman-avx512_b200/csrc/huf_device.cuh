@@ -301,7 +301,11 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
       if (i < n) sorted[rank] = mine;
     }
     __syncwarp();
-    // 3. two-queue Huffman merge: inherently serial; the queue heads live in registers
+    // 3. two-queue Huffman merge with the reference's tie rule (a leaf is preferred, :370-376):
+    //    inherently serial, so the one lane that runs it gets a branch-free body.  Queue heads
+    //    (two leaves, two nodes) live in registers, the values that could be needed after a pick
+    //    are loaded before it is decided, and whether a head exists is decided by the queue
+    //    indices, never by its value (u32 weights may wrap like the reference's, :365, :414).
     const int n_nodes = n - 1;
     if (lane == 0 && n > 1) {
       int ls = n - 1, nh = 0;
@@ -312,24 +316,23 @@ __device__ inline void build_table_warp(const CountT* hist, HufTable* tab, Table
         CountT sum = 0;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          const bool leaf = (ls >= 0) && (nh == m || L0 <= N0);  // :370-376
-          if (leaf) {
-            sum += L0;
-            sc->leaf_parent[ls] = (uint16_t)m;
-            --ls;
-            L0 = L1;
-            L1 = ls >= 1 ? (CountT)(sorted[ls - 1] >> 8) : (CountT)0;
-          } else {
-            sum += N0;
-            sc->par[0][nh] = (uint16_t)m;
-            ++nh;
-            N0 = N1;
-            N1 = nh + 1 < m ? tree[nh + 1] : (CountT)0;
-          }
+          const int li = ls - 2, ni = nh + 2;
+          const CountT l_next = (CountT)(sorted[li > 0 ? li : 0] >> 8);  // head after next, if a leaf goes
+          const CountT n_next = tree[ni < n_nodes ? ni : n_nodes - 1];   // same for the nodes (stale if >= m: fixed below)
+          const bool leaf = (ls >= 0) && (nh == m || L0 <= N0);
+          sum += leaf ? L0 : N0;
+          uint16_t* link = leaf ? &sc->leaf_parent[ls > 0 ? ls : 0] : &sc->par[0][nh];
+          *link = (uint16_t)m;
+          ls -= leaf ? 1 : 0;
+          nh += leaf ? 0 : 1;
+          L0 = leaf ? L1 : L0;
+          L1 = leaf ? l_next : L1;
+          N0 = leaf ? N0 : N1;
+          N1 = leaf ? N1 : n_next;
         }
-        tree[m] = sum;  // u32 wrap-around like the reference when CountT is u32 (:365, :414)
-        if (nh == m) N0 = sum;
-        else if (nh + 1 == m) N1 = sum;
+        tree[m] = sum;
+        N0 = nh == m ? sum : N0;  // the new node is the only / the second one waiting
+        N1 = nh + 1 == m ? sum : N1;
       }
       sc->par[0][n_nodes - 1] = (uint16_t)(n_nodes - 1);  // the root points at itself
     }
