@@ -253,7 +253,7 @@ __device__ inline void partition_phase_warp(K* a, int n, int32_t* st_first, int3
 // codes (ForallCodes, :260-284).
 // ---------------------------------------------------------------------------
 template <typename CountT, typename KeyT>
-__device__ inline void build_table_warp(const CountT* hist, HufTable* tab, TableScratch* sc) {
+__device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab, TableScratch* sc) {
   const int lane = lane_id();
   // u32 keys: keys[] in the first, the sorted copy in the second half of sc->keys, node
   // weights in sc->tree_count.  u64 keys: keys[] = sc->keys, sorted copy = sc->tree_count,
