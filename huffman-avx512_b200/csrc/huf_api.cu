@@ -277,7 +277,7 @@ struct HostTable {
   uint32_t len_mask;
   int32_t num_syms;
   uint32_t hdr_len;
-  uint32_t pad_;
+  uint32_t avg_bits_x256;
 };
 }  // namespace
 

@@ -24,7 +24,7 @@ struct HufTable {
   uint32_t len_mask;         // bit i set <=> len_count[i] != 0 (:422-426)
   int32_t num_syms;
   uint32_t hdr_len;          // 8 + popcount(len_mask) + num_syms
-  uint32_t pad_;
+  uint32_t avg_bits_x256;    // mean code length over the histogram the table was built from, 8.8 fixed point (0 = unknown)
 };
 
 // Scratch for the table build (shared memory, one per CTA).
@@ -414,6 +414,7 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
     }
     __syncwarp();
     // 6. canonical codes (ForallCodes, :260-284), one symbol per lane
+    unsigned long long bits = 0, total = 0;  // for the mean code length
     for (int i = lane; i < n; i += 32) {
       const unsigned sym = (unsigned)(sorted[i] & 0xffu);
       tab->sorted_syms[i] = (uint8_t)sym;
@@ -422,7 +423,16 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
       const uint32_t first_idx = l ? sc->cum[l - 1] : 0u;
       const uint32_t left = sc->start_code[l] + (((uint32_t)i - first_idx) << (kMaxCodeLen - l));
       tab->enc[sym] = (left >> (kMaxCodeLen - l)) | ((uint32_t)l << 16);
+      const unsigned long long cnt = (unsigned long long)hist[sym];
+      bits += cnt * (unsigned)l;
+      total += cnt;
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      bits += __shfl_xor_sync(0xffffffffu, bits, d);
+      total += __shfl_xor_sync(0xffffffffu, total, d);
+    }
+    if (lane == 0) tab->avg_bits_x256 = total ? (uint32_t)((bits << 8) / total) + 1u : 0u;  // rounded up, never 0 when known
   } else if (lane == 0) {
     for (int l = 0; l < 16; ++l) tab->len_count[l] = 0;
     tab->len_mask = 0;
@@ -430,7 +440,7 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
   }
   if (lane == 0) {
     tab->num_syms = n;
-    tab->pad_ = 0;
+    if (n == 0) tab->avg_bits_x256 = 0;
   }
   __syncwarp();
 }
@@ -453,7 +463,7 @@ __device__ inline void table_from_lengths_warp(const uint16_t* len_count, const 
     tab->len_mask = mask;
     tab->num_syms = n;
     tab->hdr_len = 8u + (uint32_t)__popc(mask) + (uint32_t)n;
-    tab->pad_ = 0;
+    tab->avg_bits_x256 = 0;  // no histogram here
   }
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
