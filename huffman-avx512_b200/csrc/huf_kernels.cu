@@ -604,12 +604,12 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
   const int warp = tid >> 5;
   const int lane = tid & 31;
   // Staged mode?  Slices of up to kStageSlice symbols always (a stream that does not fit its
-  // staging buffer falls back by itself); slices up to twice as long when the table's mean code
-  // length says that the streams fit with a margin -- compressible data does, incompressible
-  // data would only waste the attempt.  The same for every worker: geometry and table only.
+  // staging buffer falls back by itself); longer slices when the table's mean code length says
+  // that the streams fit with a margin -- compressible data does at twice the length,
+  // incompressible data would only waste the attempt.  The same for every worker: geometry and table only.
   const uint32_t slice_max = (block_size + (uint32_t)K - 1) / (uint32_t)K;
   bool staged = slice_max <= (uint32_t)kStageSlice;
-  if (!staged && slice_max <= 2u * kStageSlice && tab.avg_bits_x256 != 0) {
+  if (!staged && tab.avg_bits_x256 != 0) {
     const unsigned long long est = ((unsigned long long)slice_max * tab.avg_bits_x256) >> 8;
     staged = est <= (unsigned long long)(kStageWords - kStageFront - 2) * 28;  // 7/8 of the buffer's bits
   }
