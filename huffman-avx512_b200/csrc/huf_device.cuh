@@ -307,7 +307,75 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
     //    are loaded before it is decided, and whether a head exists is decided by the queue
     //    indices, never by its value (u32 weights may wrap like the reference's, :365, :414).
     const int n_nodes = n - 1;
-    if (lane == 0 && n > 1) {
+    // Many leaves of similar weight (incompressible input: 256 symbols, all near n/256) make the
+    // merge batchable without changing a single decision: while a node t is waiting, every leaf
+    // not heavier than t is taken before t (the rule compares the leaf with the queue's head
+    // only, and new nodes queue up behind it), so those leaves pair up among themselves, all
+    // pairs at once; and once the leaves are gone the waiting nodes pair up in queue order.
+    // Skewed inputs give batches of one, for which the serial loop below is quicker.
+    const bool batched = n >= 32 && (CountT)(sorted[n / 2] >> 8) <= 4 * (CountT)(sorted[n - 1] >> 8);
+    if (batched) {
+      auto W = [&](int i) { return (CountT)(sorted[n - 1 - i] >> 8); };  // leaves in ascending order
+      int q = 0, nh = 0, m = 0;  // next leaf, head of the node queue, nodes made (all warp-uniform)
+      while (m < n_nodes) {
+        if (nh == m) {  // no node waiting: two leaves
+          if (lane == 0) {
+            tree[m] = W(q) + W(q + 1);
+            sc->leaf_parent[n - 1 - q] = (uint16_t)m;
+            sc->leaf_parent[n - 2 - q] = (uint16_t)m;
+          }
+          q += 2;
+          m += 1;
+        } else if (q == n) {  // leaves used up: the waiting nodes pair up in order
+          int p = (m - nh) >> 1;
+          p = p < 32 ? p : 32;
+          if (lane < p) {
+            tree[m + lane] = tree[nh + 2 * lane] + tree[nh + 2 * lane + 1];
+            sc->par[0][nh + 2 * lane] = (uint16_t)(m + lane);
+            sc->par[0][nh + 2 * lane + 1] = (uint16_t)(m + lane);
+          }
+          nh += 2 * p;
+          m += p;
+        } else {
+          const CountT t = tree[nh];
+          const int idx = q + lane;
+          const int c = __popc(__ballot_sync(0xffffffffu, idx < n && W(idx < n ? idx : 0) <= t));  // a prefix: the leaves ascend
+          if (c >= 2) {  // c / 2 leaf pairs at once
+            const int p = c >> 1;
+            if (lane < p) {
+              tree[m + lane] = W(q + 2 * lane) + W(q + 2 * lane + 1);
+              sc->leaf_parent[n - 1 - (q + 2 * lane)] = (uint16_t)(m + lane);
+              sc->leaf_parent[n - 2 - (q + 2 * lane)] = (uint16_t)(m + lane);
+            }
+            q += 2 * p;
+            m += p;
+          } else if (c == 1) {  // the last such leaf, then t itself
+            if (lane == 0) {
+              tree[m] = W(q) + t;
+              sc->leaf_parent[n - 1 - q] = (uint16_t)m;
+              sc->par[0][nh] = (uint16_t)m;
+            }
+            q += 1;
+            nh += 1;
+            m += 1;
+          } else {  // t first, then whatever the rule picks (:370-376)
+            const int nh1 = nh + 1;
+            const bool leaf2 = nh1 == m || W(q) <= tree[nh1 < n_nodes ? nh1 : 0];
+            if (lane == 0) {
+              sc->par[0][nh] = (uint16_t)m;
+              if (leaf2) sc->leaf_parent[n - 1 - q] = (uint16_t)m;
+              else sc->par[0][nh1] = (uint16_t)m;
+              tree[m] = t + (leaf2 ? W(q) : tree[nh1]);
+            }
+            q += leaf2 ? 1 : 0;
+            nh += leaf2 ? 1 : 2;
+            m += 1;
+          }
+        }
+        __syncwarp();
+      }
+      if (lane == 0) sc->par[0][n_nodes - 1] = (uint16_t)(n_nodes - 1);  // the root points at itself
+    } else if (lane == 0 && n > 1) {
       int ls = n - 1, nh = 0;
       CountT L0 = (CountT)(sorted[ls] >> 8);
       CountT L1 = (CountT)(sorted[ls - 1] >> 8);

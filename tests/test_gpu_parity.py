@@ -275,6 +275,13 @@ def test_table_build_sort_order_stress(huf, oracle):
                     vals[half + i] = 2 * (i + 1)
             h[:n] = vals[:n]
             hists.append(h)
+    # similar weights (what incompressible input looks like): the batched form of the two-queue
+    # merge; with counts near 2^31 the u32 node weights wrap like the reference's
+    for n in (32, 33, 64, 100, 255, 256):
+        for base, spread in ((500, 40), (3, 2), (1 << 20, 1 << 18), ((1 << 31) - 100, 90)):
+            h = np.zeros(256, dtype=np.uint32)
+            h[rng.permutation(256)[:n]] = (base + rng.integers(-spread, spread + 1, n)).astype(np.uint32)
+            hists.append(h)
     for t, h in enumerate(hists):
         want = oracle.make_coding(h)
         got = huf.make_table(h)
