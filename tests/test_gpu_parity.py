@@ -288,3 +288,28 @@ def test_table_build_sort_order_stress(huf, oracle):
         assert got["sorted_syms"] == want["sorted_syms"], t
         assert np.array_equal(got["len_count"], want["len_count"]), t
         assert np.array_equal(got["code_bits"], want["code_bits"]), t
+
+
+def test_staged_mode_for_long_slices_and_its_fallback(huf, oracle):
+    """Slices of 8192 symbols are staged when the table's mean code length says the streams fit
+    their staging buffers; a stream that does not fit after all takes the ring path, and a block
+    whose mean says 'no' is not staged at all.  Bytes equal the oracle either way."""
+    rng = np.random.default_rng(5)
+    k, bs = 16, 131072
+    sl = bs // k
+    assert sl == 8192
+    mostly = np.full(bs, ord("a"), dtype=np.uint8)
+    mostly[::5] = ord("b")
+    one_hot = mostly.copy()
+    one_hot[5 * sl:6 * sl] = rng.integers(0, 256, sl, dtype=np.uint8)  # one incompressible slice
+    noise = rng.integers(0, 256, bs, dtype=np.uint8)                    # mean code length 8: ring path
+    for blk in (mostly, one_hot, noise):
+        data = blk.tobytes()
+        want = oracle.compress(k, data)
+        assert huf.compress(k, data) == want
+    data = mostly.tobytes() + one_hot.tobytes() + noise.tobytes() + one_hot.tobytes()[:70001]
+    assert huf.decompress_blocks(huf.compress_blocks(k, bs, data)) == data
+    # the incompressible slice really overflows a staging buffer (1276 words) while the block's mean is low
+    cd = oracle.make_coding(oracle.histogram(one_hot.tobytes()))
+    assert int(cd["code_len"][one_hot[5 * sl:6 * sl]].sum()) > 1276 * 32
+    assert int(cd["code_len"][one_hot].sum()) / bs * sl < 1276 * 28
