@@ -455,10 +455,10 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_bas
 // enc_addr: shared-space address of the encode table (entry = code | len << 16).
 __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr, uint32_t stage_base,
                                                                const uint8_t* sp, uint32_t sz, bool* overflow,
-                                                               const uint8_t* lim) {
+                                                               const uint8_t* lim, uint32_t bitpos0 = 0) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
-  uint32_t bitpos = 0;  // a staged stream is at most kStageSlice * 12 bits long
+  uint32_t bitpos = bitpos0;  // where the first code goes (long streams are staged piecewise, see below); the end position is returned
   bool over = false;
   uint32_t sb = stage_base + 4u * kStageFront;  // stream word 0
   auto entry = [&](uint32_t w, int i) { return lds_u32_ro(entry_addr(enc_addr, byte_of(w, i))); };
@@ -593,6 +593,77 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
   __syncwarp();
 }
 
+// Long streams (a slice that does not fit a staging buffer): the stream's bit total and with it
+// its place are known from a first pass, and the stream is staged and written out piece by piece.
+// A piece of kPieceSyms symbols fits the buffer whatever its codes are; it is encoded starting at
+// the bit position the previous piece ended on (mod 32), on top of that piece's last, partial word
+// which stays behind as word 0 -- so the buffer always holds whole stream words, and the row
+// formula of copy_stream_out_warp applies with a word offset.
+constexpr uint32_t kPieceSyms = 3072;
+static_assert(kPieceSyms % 512 == 0 && kPieceSyms * 12 + 31 <= (uint32_t)(kStageWords - kStageFront - 2) * 32,
+              "a piece always fits");
+
+// Buffer words [0, nw_emit) go out as stream words m_base.. (words from nw_data on are zero:
+// padding and slop of the last piece); the words read are zeroed.  wend = word address of the
+// region's aligned end, carry = stream word m_base - 1.
+__device__ inline void copy_words_out_warp(uint32_t sb, uint32_t nw_data, uint32_t nw_emit, uint32_t* wend,
+                                               uint32_t m_base, uint32_t sh, uint32_t carry) {
+  const int lane = lane_id();
+  for (uint32_t i0 = 0; i0 < nw_emit; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    uint32_t lo = 0;
+    if (i < nw_data) {
+      lo = lds_u32(sb + 4u * i);
+      sts_u32(sb + 4u * i, 0);
+    }
+    uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
+    if (lane == 0) hi = carry;
+    if (i < nw_emit) *(wend - (m_base + i)) = __funnelshift_lc(lo, hi, sh);
+    carry = __shfl_sync(0xffffffffu, lo, 31);  // only full rows are followed by another row
+  }
+}
+
+__device__ inline void encode_long_stream_warp(uint32_t enc_addr, uint32_t stage_base, const uint8_t* sp, uint32_t sz,
+                                               uint8_t* dst, uint32_t e_off, uint32_t region, const uint8_t* lim) {
+  const int lane = lane_id();
+  const uint32_t r = ((e_off - 1u) & 3u) + 1u;
+  const uint32_t sh = 8u * r;
+  const uint32_t e_al = e_off - r;
+  const uint32_t s_al = (e_off - region + 3u) & ~3u;
+  const uint32_t m_last = (e_al - s_al) >> 2;  // inclusive
+  uint32_t* wend = reinterpret_cast<uint32_t*>(dst + e_al);
+  const uint32_t sb = stage_base + 4u * kStageFront;
+  uint32_t b = 0, m_base = 0, carry = 0;
+  uint32_t off = 0;
+  do {
+    const uint32_t piece = sz - off < kPieceSyms ? sz - off : kPieceSyms;
+    const bool last = off + piece == sz;
+    bool over;
+    const uint32_t endbit = (uint32_t)encode_stream_staged_warp(enc_addr, stage_base, sp + off, piece, &over, lim, b);
+    if (!last) {
+      const uint32_t nfull = endbit >> 5;
+      // the last data word of this piece is needed as the next row's carry: read it before it is zeroed
+      const uint32_t tail_word = nfull ? lds_u32(sb + 4u * (nfull - 1)) : carry;
+      __syncwarp();
+      copy_words_out_warp(sb, nfull, nfull, wend, m_base, sh, carry);
+      carry = tail_word;
+      __syncwarp();
+      if (lane == 0 && nfull != 0) {  // the partial word becomes word 0 of the next piece
+        const uint32_t pw = lds_u32(sb + 4u * nfull);
+        sts_u32(sb + 4u * nfull, 0);
+        sts_u32(sb, pw);
+      }
+      __syncwarp();
+      m_base += nfull;
+      b = endbit & 31u;
+    } else {
+      copy_words_out_warp(sb, (endbit + 31u) >> 5, m_last - m_base + 1u, wend, m_base, sh, carry);
+    }
+    off += piece;
+  } while (off < sz);
+  __syncwarp();
+}
+
 // Worker-only barrier (named barrier 1): the table-builder warp never takes part in it.
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory"); }
 
@@ -716,8 +787,8 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
         geom(s, st, sz);
         const uint32_t e_off = hdr_total + sm.region_end[s];
         const uint32_t region = sm.region_end[s] - (s ? sm.region_end[s - 1] : 0u);
-        encode_stream_warp(tab.enc, smem_u32(&sm.u.ring[warp][0]), src + st, sz, sm.stream_bits[s], dst, e_off,
-                           region, raw + n);
+        encode_long_stream_warp(smem_u32(tab.enc), smem_u32(&sm.u.stage[warp][0]), src + st, sz, dst, e_off, region,
+                                raw + n);
       }
     }
     worker_sync();
