@@ -453,12 +453,13 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_bas
 // the previous copy-out).  Returns the stream's bit total; *overflow is set when it does not fit
 // (then only the count is valid and the caller falls back to the ring path).
 // enc_addr: shared-space address of the encode table (entry = code | len << 16).
+template <bool kPiece = false>
 __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr, uint32_t stage_base,
                                                                const uint8_t* sp, uint32_t sz, bool* overflow,
                                                                const uint8_t* lim, uint32_t bitpos0 = 0) {
   const int lane = lane_id();
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
-  uint32_t bitpos = bitpos0;  // where the first code goes (long streams are staged piecewise, see below); the end position is returned
+  uint32_t bitpos = kPiece ? bitpos0 : 0u;  // where the first code goes (long streams are staged piecewise, see below); the end position is returned
   bool over = false;
   uint32_t sb = stage_base + 4u * kStageFront;  // stream word 0
   auto entry = [&](uint32_t w, int i) { return lds_u32_ro(entry_addr(enc_addr, byte_of(w, i))); };
@@ -639,7 +640,7 @@ __device__ inline void encode_long_stream_warp(uint32_t enc_addr, uint32_t stage
     const uint32_t piece = sz - off < kPieceSyms ? sz - off : kPieceSyms;
     const bool last = off + piece == sz;
     bool over;
-    const uint32_t endbit = (uint32_t)encode_stream_staged_warp(enc_addr, stage_base, sp + off, piece, &over, lim, b);
+    const uint32_t endbit = (uint32_t)encode_stream_staged_warp<true>(enc_addr, stage_base, sp + off, piece, &over, lim, b);
     if (!last) {
       const uint32_t nfull = endbit >> 5;
       // the last data word of this piece is needed as the next row's carry: read it before it is zeroed
@@ -668,6 +669,10 @@ __device__ inline void encode_long_stream_warp(uint32_t enc_addr, uint32_t stage
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory"); }
 
 // Everything the workers do for one block once its table is in `tab`: header, streams, sizes.
+// kLongSlices = false: every slice has at most kStageSlice symbols (decided at launch from the
+// geometry), so only the staged mode and its per-stream fallback are compiled in -- the kernel of
+// the common shapes carries no code for long streams.
+template <bool kLongSlices>
 __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, const uint8_t* raw, uint64_t n,
                                             const uint8_t* src, uint32_t bn, uint32_t block_size, int K,
                                             uint8_t* dst, uint32_t* comp_size_out, uint32_t* status) {
@@ -679,8 +684,8 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
   // that the streams fit with a margin -- compressible data does at twice the length,
   // incompressible data would only waste the attempt.  The same for every worker: geometry and table only.
   const uint32_t slice_max = (block_size + (uint32_t)K - 1) / (uint32_t)K;
-  bool staged = slice_max <= (uint32_t)kStageSlice;
-  if (!staged && tab.avg_bits_x256 != 0) {
+  bool staged = !kLongSlices || slice_max <= (uint32_t)kStageSlice;
+  if (kLongSlices && !staged && tab.avg_bits_x256 != 0) {
     const unsigned long long est = ((unsigned long long)slice_max * tab.avg_bits_x256) >> 8;
     staged = est <= (unsigned long long)(kStageWords - kStageFront - 2) * 28;  // 7/8 of the buffer's bits
   }
@@ -764,8 +769,8 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
       }
     }
     worker_sync();
-  } else {
-    // ---- ring mode (long slices): per-stream bit totals first (:772-782)
+  } else if constexpr (kLongSlices) {
+    // ---- long slices: per-stream bit totals first (:772-782)
     for (int s = warp; s < K; s += kCompWarps) {
       uint32_t st, sz;
       geom(s, st, sz);
@@ -822,6 +827,7 @@ __device__ uint32_t g_comp_counters[kCounterSlots][2];
 // the workers encode block b with table[cur], the builder turns the histogram of the CTA's next
 // block (counted by the workers just before) into table[cur^1]; its ~6k serial instructions
 // disappear behind the encode.
+template <bool kLongSlices>
 __global__ void __launch_bounds__(kCompThreads, kCompCtasPerSm)
 k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_size, int K,
                   uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
@@ -902,7 +908,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
           if (tid < 256 && sm.hist[cur][tid] != 0 && sm.tab[cur].enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
         }
         const uint64_t boff = (uint64_t)b * block_size;
-        encode_block_workers(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
+        encode_block_workers<kLongSlices>(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
                              out + (uint64_t)b * slot_stride, comp_sizes + b, status);
       }
       __syncthreads();
@@ -1447,20 +1453,22 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
                             uint8_t* d_out, uint64_t slot_stride, uint32_t* d_sizes, const void* d_table,
                             int check_presence, uint32_t* d_status, int grid, cudaStream_t st) {
   if (n_blocks == 0) return cudaSuccess;
-  // the attribute is per device: remember for which one it has been set (bit per ordinal)
-  static thread_local unsigned long long configured = 0;
+  // two builds of the kernel: slices of at most kStageSlice symbols (no long-stream code), and the rest
+  const bool long_slices = (block_size + (uint32_t)K - 1) / (uint32_t)K > (uint32_t)kStageSlice;
+  auto kernel = long_slices ? k_compress_blocks<true> : k_compress_blocks<false>;
+  // the attribute is per device and per kernel: remember where it has been set (bit per ordinal)
+  static thread_local unsigned long long configured[2] = {0, 0};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev >= 64 || !((configured >> dev) & 1ull)) {
-    e = cudaFuncSetAttribute(k_compress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompSmem));
+  if (dev >= 64 || !((configured[long_slices] >> dev) & 1ull)) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompSmem));
     if (e != cudaSuccess) return e;
-    if (dev < 64) configured |= 1ull << dev;
+    if (dev < 64) configured[long_slices] |= 1ull << dev;
   }
-  k_compress_blocks<<<grid, kCompThreads, sizeof(CompSmem), st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride,
-                                                   d_sizes, reinterpret_cast<const HufTable*>(d_table),
-                                                   check_presence, d_status,
-                                                   g_counter_slot.fetch_add(1, std::memory_order_relaxed) % kCounterSlots);
+  kernel<<<grid, kCompThreads, sizeof(CompSmem), st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride, d_sizes,
+                                                       reinterpret_cast<const HufTable*>(d_table), check_presence, d_status,
+                                                       g_counter_slot.fetch_add(1, std::memory_order_relaxed) % kCounterSlots);
   return cudaGetLastError();
 }
 
