@@ -3,7 +3,8 @@
 //   k_histogram          byte histogram, lane-privatised shared-memory bins, 128-bit loads
 //   k_build_table        canonical table from a 256 x u64 histogram (shared-table mode)
 //   k_make_table         same from a u32 histogram, dumping every field (ABI/table parity)
-//   k_compress_blocks    fused per-block histogram -> table -> stream lengths -> encode
+//   k_compress_blocks    fused per-block histogram -> table -> encode (staged in shared memory; long
+//                        streams piecewise after a length pass); warp-specialised, blocks handed out dynamically
 //   k_decompress_blocks  header parse -> multi-symbol table (2 symbols x 12 bits = the reference's
 //                        Decoder2x; the kernel uses 3 symbols x 11 bits) -> one lane per stream decode
 //   k_dump_dtable        the decode kernel's table builder, for parity tests
@@ -161,17 +162,16 @@ __global__ void __launch_bounds__(32) k_make_table(const uint32_t* __restrict__ 
 // ===========================================================================
 // Fused compress kernel: one CTA per block (CompressMulti<K>, codec/huffman.cpp:738-846)
 // ===========================================================================
-constexpr int kRingWords = 256;  // per-warp staging ring, in 32-bit stream words (1 KiB, 1 KiB-aligned)
 // Staged mode (slices of at most kStageSlice symbols): a warp keeps the whole bitstream of its
 // stream in shared memory, so the stream's size is known without a separate length pass.
 constexpr int kStageSlice = 4096;
-constexpr int kStageWords = 1280;  // 5 KiB per warp = 10 bits/symbol; longer streams take the ring path
+constexpr int kStageWords = 1280;  // 5 KiB per warp = 10 bits/symbol of a 4096-symbol slice; the first 256 words (1 KiB-aligned)
+                                   // double as the ring of the per-stream fallback encoder
 constexpr int kStageFront = 2;     // spare words before stream word 0 (see stage_put64_end)
 
 struct CompSmem {
   union {
     uint32_t bins[256 * 32];                  // histogram phase
-    uint32_t ring[kCompWarps][kRingWords];    // encode phase, ring mode
     uint32_t stage[kCompWarps][kStageWords];  // encode phase, staged mode (each 1 KiB-aligned)
   } u;
   uint32_t hist[2][256];  // [cur] block being encoded, [cur^1] the CTA's next block
