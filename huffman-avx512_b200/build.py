@@ -6,7 +6,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libhufb200.so")
+# HUFB200_LIB: tuning sweeps load a prebuilt variant (never set in production)
+LIB = os.environ.get("HUFB200_LIB") or os.path.join(HERE, "libhufb200.so")
 SOURCES = ["huf_kernels.cu", "huf_api.cu"]
 HEADERS = ["huf_device.cuh", "huf_kernels.h", os.path.join("..", "..", "include", "hufb200.h")]
 NVCC_FLAGS = [

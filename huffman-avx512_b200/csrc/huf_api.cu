@@ -272,6 +272,7 @@ namespace {
 // mirrors hufb200::HufTable (huf_device.cuh) for the host-side dump
 struct HostTable {
   uint32_t enc[256];
+  uint32_t enc2[256];
   uint8_t sorted_syms[256];
   uint16_t len_count[16];
   uint32_t len_mask;

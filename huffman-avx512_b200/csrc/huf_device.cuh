@@ -14,11 +14,15 @@ constexpr int kMaxCodeLen = 12;   // kMaxCodeLength, codec/huffman.cpp:38
 constexpr int kSlop = 8;          // kSlop, codec/huffman.cpp:770
 constexpr int kMaxK = 64;
 constexpr uint32_t kEncInvalid = 0x10000000u;  // enc[] entry of a symbol without a code
+constexpr uint32_t kEnc2Invalid = 1u << 12;    // enc2[] entry of such a symbol: no bits, a marker that survives the entry sums
 
 // Encode-side table.  Lives in shared memory (per-block tables) or in global
 // memory (shared-table mode, built by k_build_table).
 struct HufTable {
   uint32_t enc[256];         // code right-aligned in bits 0..11, length in bits 16..19
+  uint32_t enc2[256];        // the same codes for the staged encoder: code << (32 - len) | len (code top-aligned,
+                             // length in bits 0..3, bits 4..19 zero); kEnc2Invalid for a symbol without a code.
+                             // Must follow enc directly (the encoder reads it at enc + 1 KiB).
   uint8_t sorted_syms[256];  // canonical order (CanonicalCoding::sorted_syms, :288)
   uint16_t len_count[16];    // [0..12] used (CanonicalCoding::len_count, :290)
   uint32_t len_mask;         // bit i set <=> len_count[i] != 0 (:422-426)
@@ -271,7 +275,10 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
     if (cnt != 0) keys[n + __popc(m & ((1u << lane) - 1))] = ((KeyT)cnt << 8) | (KeyT)c;
     n += __popc(m);
   }
-  for (int i = lane; i < 256; i += 32) tab->enc[i] = kEncInvalid;
+  for (int i = lane; i < 256; i += 32) {
+    tab->enc[i] = kEncInvalid;
+    tab->enc2[i] = kEnc2Invalid;
+  }
   for (int i = lane; i < 36; i += 32) sc->len_count33[i] = 0;
   __syncwarp();
 
@@ -491,6 +498,7 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
       const uint32_t first_idx = l ? sc->cum[l - 1] : 0u;
       const uint32_t left = sc->start_code[l] + (((uint32_t)i - first_idx) << (kMaxCodeLen - l));
       tab->enc[sym] = (left >> (kMaxCodeLen - l)) | ((uint32_t)l << 16);
+      tab->enc2[sym] = (left << (32 - kMaxCodeLen)) | (uint32_t)l;
       const unsigned long long cnt = (unsigned long long)hist[sym];
       bits += cnt * (unsigned)l;
       total += cnt;
@@ -517,7 +525,10 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
 __device__ inline void table_from_lengths_warp(const uint16_t* len_count, const uint8_t* syms,
                                                int n, HufTable* tab, TableScratch* sc) {
   const int lane = lane_id();
-  for (int i = lane; i < 256; i += 32) tab->enc[i] = kEncInvalid;
+  for (int i = lane; i < 256; i += 32) {
+    tab->enc[i] = kEncInvalid;
+    tab->enc2[i] = kEnc2Invalid;
+  }
   if (lane == 0) {
     uint32_t cum = 0, code = 0, mask = 0;
     for (int l = 0; l <= kMaxCodeLen; ++l) {
@@ -542,6 +553,7 @@ __device__ inline void table_from_lengths_warp(const uint16_t* len_count, const 
     const uint32_t first_idx = l ? sc->cum[l - 1] : 0u;
     const uint32_t left = sc->start_code[l] + (((uint32_t)i - first_idx) << (kMaxCodeLen - l));
     tab->enc[sym] = (left >> (kMaxCodeLen - l)) | ((uint32_t)l << 16);
+    tab->enc2[sym] = (left << (32 - kMaxCodeLen)) | (uint32_t)l;
   }
   __syncwarp();
 }

@@ -61,8 +61,44 @@ __device__ __forceinline__ uint32_t bins_reduce_clear(uint32_t* bins, int t) {
   return s;
 }
 
+// L2 eviction-priority hints (experiment HUF_L2HINT): a block is read twice by the compress
+// kernel -- first for its histogram (kept: evict_last), then for the encode (dropped: evict_first).
+#ifndef HUF_L2HINT
+#define HUF_L2HINT 0
+#endif
+__device__ __forceinline__ unsigned long long l2_policy_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+template <int kHint>  // 0 none, 1 evict_last, 2 evict_first
+__device__ __forceinline__ uint4 ldg128(const uint4* a) {
+  if (kHint == 0) return *a;
+  uint4 v;
+  const unsigned long long pol = kHint == 1 ? l2_policy_last() : l2_policy_first();
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(a), "l"(pol));
+  return v;
+}
+template <int kHint>
+__device__ __forceinline__ void stg32(uint32_t* a, uint32_t v) {
+  if (kHint == 0) {
+    *a = v;
+    return;
+  }
+  const unsigned long long pol = l2_policy_first();
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+
 // Accumulates the bytes [p, p+n) into the CTA's lane-private bins (all threads).
 // (t, nt): index of the calling thread among the nt threads that take part (whole warps).
+template <int kHint = 0>
 __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p, uint64_t n, uint32_t t, uint32_t nt) {
   uint32_t* bl = bins + lane_id();
   const uint64_t mis = (16 - ((uintptr_t)p & 15)) & 15;
@@ -73,10 +109,12 @@ __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p
   uint64_t i = t;
   const uint64_t step = nt;
   if (i + 3 * step < nvec) {  // batches of 4 loads per thread, the next batch in flight while one is counted
-    uint4 a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
+    uint4 a = ldg128<kHint>(v + i), b = ldg128<kHint>(v + i + step), c = ldg128<kHint>(v + i + 2 * step),
+          d = ldg128<kHint>(v + i + 3 * step);
     i += 4 * step;
     for (; i + 3 * step < nvec; i += 4 * step) {
-      const uint4 a2 = v[i], b2 = v[i + step], c2 = v[i + 2 * step], d2 = v[i + 3 * step];
+      const uint4 a2 = ldg128<kHint>(v + i), b2 = ldg128<kHint>(v + i + step), c2 = ldg128<kHint>(v + i + 2 * step),
+                  d2 = ldg128<kHint>(v + i + 3 * step);
       bins_add_vec(bl, a);
       bins_add_vec(bl, b);
       bins_add_vec(bl, c);
@@ -91,7 +129,7 @@ __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p
     bins_add_vec(bl, c);
     bins_add_vec(bl, d);
   }
-  for (; i < nvec; i += step) bins_add_vec(bl, v[i]);
+  for (; i < nvec; i += step) bins_add_vec(bl, ldg128<kHint>(v + i));
   const uint64_t done = head + (nvec << 4);
   for (uint64_t j = done + t; j < n; j += nt) atomicAdd(bl + ((uint32_t)p[j] << 5), 1u);
 }
@@ -449,10 +487,104 @@ __device__ inline void encode_stream_warp(const uint32_t* enc, uint32_t ring_bas
   __syncwarp();
 }
 
+// ---- staged encoder -------------------------------------------------------------------------
+// What the staging puts may touch: every put stays inside [stream word -2, stream word
+// kStageLimitBits/32 + 2).
+constexpr uint32_t kStageLimitBits = (uint32_t)(kStageWords - kStageFront - 2) * 32;
+
+__device__ __forceinline__ uint32_t lds_u32_ro_enc2(uint32_t addr) {  // entry of HufTable::enc2 (1 KiB behind enc)
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1+1024];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void red_or_shared_off(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.or.b32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+// Up to 64 bits, TOP-aligned in hi:lo (first bit = bit 31 of hi, everything behind the last bit
+// zero), whose first bit goes to stream bit position `pos`: with r = pos % 32 the three words
+// from word pos/32 on receive hi >> r, (hi:lo) >> r and lo << (32 - r) -- three funnel shifts
+// that take pos as it is (the hardware uses pos % 32).
+__device__ __forceinline__ void stage_put64_start(uint32_t stream_base, uint32_t pos, uint32_t hi, uint32_t lo) {
+  const uint32_t a = entry_addr(stream_base, pos >> 5);
+  red_or_shared_off<0>(a, __funnelshift_r(hi, 0u, pos));
+  red_or_shared_off<4>(a, __funnelshift_r(lo, hi, pos));
+  red_or_shared_off<8>(a, __funnelshift_r(0u, lo, pos));  // 0 for r == 0
+}
+
+// One trip (16 symbols per lane) the general way: entries of HufTable::enc (code | len << 16),
+// pair and quad codes right-aligned, 64-bit puts when every quad has at most 32 bits, else quad by
+// quad.  Any code lengths.  Kept out of line: the staged encoder below takes it only when a quad
+// is longer than 32 bits.
+// Takes and returns the running bit position with the overflow flag in bit 31 (by value: a
+// reference into the caller's frame would pin those variables to local memory).
+__device__ __noinline__ uint32_t encode_trip_general(uint32_t enc_addr, uint32_t sb, uint32_t w0, uint32_t w1,
+                                                     uint32_t w2, uint32_t w3, uint32_t valid, uint32_t state) {
+  uint32_t bitpos = state & 0x7fffffffu;
+  bool over = (state >> 31) != 0;
+  const uint32_t w[4] = {w0, w1, w2, w3};
+  uint32_t c01[4], l01[4], c23[4], l23[4], lq[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      e[i] = (uint32_t)(4 * j + i) < valid ? lds_u32_ro(entry_addr(enc_addr, byte_of(w[j], i))) : 0u;
+    quad_code<true>(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
+    lq[j] = l01[j] + l23[j];
+  }
+  const uint32_t lane_len = (lq[0] + lq[1]) + (lq[2] + lq[3]);
+  const uint32_t incl = warp_incl_scan(lane_len);
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  // a symbol without a code makes `total` huge and lands here as an overflow, too
+  if (bitpos + total > kStageLimitBits) over = true;
+  const uint32_t longest = max(max(lq[0], lq[1]), max(lq[2], lq[3]));
+  uint32_t pos = bitpos + (incl - lane_len);
+  if (!over && longest <= 32u) {
+#pragma unroll
+    for (int h = 0; h < 4; h += 2) {
+      const uint32_t qa = (c01[h] << l23[h]) | c23[h];
+      const uint32_t qb = (c01[h + 1] << l23[h + 1]) | c23[h + 1];
+      pos += lq[h] + lq[h + 1];
+      stage_put64_end(sb, pos, __funnelshift_lc(qa, 0u, lq[h + 1]), shl_c(qa, lq[h + 1]) | qb);
+    }
+  } else if (!over) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (lq[j] <= 32) {
+        stage_put(sb, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
+      } else {
+        stage_put(sb, pos, c01[j], l01[j]);
+        stage_put(sb, pos + l01[j], c23[j], l23[j]);
+      }
+      pos += lq[j];
+    }
+  }
+  bitpos += total;
+  if (bitpos > 0x7fffffffu) bitpos = 0x7fffffffu;  // (over is set long before)
+  return bitpos | (over ? 0x80000000u : 0u);
+}
+
 // Staged mode, step 1: encode the whole stream into the warp's linear staging buffer (zeroed by
-// the previous copy-out).  Returns the stream's bit total; *overflow is set when it does not fit
-// (then only the count is valid and the caller falls back to the ring path).
-// enc_addr: shared-space address of the encode table (entry = code | len << 16).
+// the previous copy-out).  Returns the stream's bit total (all ones if a symbol has no code);
+// *overflow is set when it does not fit (then only the count is valid and the caller falls back
+// to the ring path).  enc_addr: shared-space address of the HufTable (enc, then enc2).
+//
+// A trip handles 512 symbols, 16 per lane (one 128-bit load), with the entries of enc2:
+// code << (32 - len) | len, i.e. the code TOP-aligned and its length in the low bits, bits
+// 4..19 zero.  Then
+//   * a funnel shift takes its amount from the low 5 bits of a register, so "append code b behind
+//     code a" is a | (b >> a) with the ENTRY a as the shift amount -- no length is ever
+//     extracted -- and the pair's length is the low bits of a + b (the sums of up to 16 entries
+//     keep the length total exact in bits 0..7: nothing carries into them);
+//   * pair = (e0 | e1 >> e0) & ~15 (the AND, free inside the same LOP3, drops the length bits),
+//     quad = pair01 | pair23 >> (e0 + e1): 9 instructions for four symbols, exact whenever the
+//     quad has at most 32 bits;
+//   * two quads make a top-aligned 64-bit value that goes to the lane's scanned bit position with
+//     three red.shared.or (stage_put64_start).
+// A trip in which some lane has a quad longer than 32 bits (a warp vote) is redone the general
+// way (encode_trip_general); so are streams of symbols without a code, which the marker bit of
+// their enc2 entry exposes in the entry sums.
 template <bool kPiece = false>
 __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr, uint32_t stage_base,
                                                                const uint8_t* sp, uint32_t sz, bool* overflow,
@@ -461,49 +593,57 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   const bool aligned = (((uintptr_t)sp) & 15) == 0;
   uint32_t bitpos = kPiece ? bitpos0 : 0u;  // where the first code goes (long streams are staged piecewise, see below); the end position is returned
   bool over = false;
+  uint32_t flag = 0;  // OR of the entry sums: bits 12..16 set <=> some symbol had no code
   uint32_t sb = stage_base + 4u * kStageFront;  // stream word 0
-  auto entry = [&](uint32_t w, int i) { return lds_u32_ro(entry_addr(enc_addr, byte_of(w, i))); };
-  // 16 symbols per lane: entries -> quad codes -> two 64-bit puts at the lane's scanned position
-  auto encode16 = [&](const uint32_t (&c01)[4], const uint32_t (&l01)[4], const uint32_t (&c23)[4],
-                      const uint32_t (&l23)[4]) {
-    uint32_t lq[4];
+  auto entry2 = [&](uint32_t w, int i) { return lds_u32_ro_enc2(entry_addr(enc_addr, byte_of(w, i))); };
+  // kFull: every lane has 16 symbols; else `valid` of them (symbols past the slice's end contribute no bits)
+  auto trip = [&](const uint4& v, auto full_tag, uint32_t valid) {
+    constexpr bool kFull = decltype(full_tag)::value;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t Q[4], S[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) lq[j] = l01[j] + l23[j];
-    const uint32_t lane_len = (lq[0] + lq[1]) + (lq[2] + lq[3]);
+    for (int j = 0; j < 4; ++j) {
+      uint32_t e[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) e[i] = (kFull || (uint32_t)(4 * j + i) < valid) ? entry2(w[j], i) : 0u;
+      const uint32_t s01 = e[0] + e[1];
+      S[j] = s01 + (e[2] + e[3]);
+      const uint32_t p01 = (e[0] | __funnelshift_r(e[1], 0u, e[0])) & ~15u;
+      const uint32_t p23 = (e[2] | __funnelshift_r(e[3], 0u, e[2])) & ~15u;
+      Q[j] = p01 | __funnelshift_r(p23, 0u, s01);
+    }
+    const uint32_t sA = S[0] + S[1], sB = S[2] + S[3];
+    const uint32_t T = sA + sB;
+    flag |= T;
+    // quad longer than 32 bits <=> bit 6 of (its length + 31); lengths sit in bits 0..5 of S
+    const uint32_t chk = ((S[0] + 31u) | (S[1] + 31u)) | ((S[2] + 31u) | (S[3] + 31u));
+    if (__any_sync(0xffffffffu, (chk & 0x40u) != 0)) {
+      const uint32_t st = encode_trip_general(enc_addr, sb, w[0], w[1], w[2], w[3], kFull ? 16u : valid,
+                                              bitpos | (over ? 0x80000000u : 0u));
+      bitpos = st & 0x7fffffffu;
+      over = (st >> 31) != 0;
+      return;
+    }
+    const uint32_t lane_len = T & 0xffu;
     const uint32_t incl = warp_incl_scan(lane_len);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    // a symbol without a code makes `total` huge and lands here as an overflow, too
-    if (bitpos + total > (uint32_t)(kStageWords - kStageFront - 2) * 32) over = true;  // puts touch up to 3 words
-    // one decision per lane and trip: all four quads at most 32 bits long (practically always)
-    // -> two 64-bit puts; else the quads one by one
-    const uint32_t longest = max(max(lq[0], lq[1]), max(lq[2], lq[3]));
-    uint32_t pos = bitpos + (incl - lane_len);
-    if (!over && longest <= 32u) {
+    if (bitpos + total > kStageLimitBits) over = true;  // the same in every lane
+    if (!over) {
+      uint32_t pos = bitpos + (incl - lane_len);
 #pragma unroll
       for (int h = 0; h < 4; h += 2) {
-        const uint32_t qa = (c01[h] << l23[h]) | c23[h];
-        const uint32_t qb = (c01[h + 1] << l23[h + 1]) | c23[h + 1];
-        pos += lq[h] + lq[h + 1];
-        stage_put64_end(sb, pos, __funnelshift_lc(qa, 0u, lq[h + 1]), shl_c(qa, lq[h + 1]) | qb);
-      }
-    } else if (!over) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (lq[j] <= 32) {
-          stage_put(sb, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
-        } else {
-          stage_put(sb, pos, c01[j], l01[j]);
-          stage_put(sb, pos + l01[j], c23[j], l23[j]);
-        }
-        pos += lq[j];
+        const uint32_t a = S[h] & 0x3fu;  // 0..32: clamping shifts
+        stage_put64_start(sb, pos, Q[h] | __funnelshift_rc(Q[h + 1], 0u, a), __funnelshift_rc(0u, Q[h + 1], a));
+        if (h == 0) pos += sA & 0x7fu;
       }
     }
     bitpos += total;
   };
 
   // full groups of 512 symbols: every lane has 16, nothing to mask; the next group's symbols are
-  // requested one iteration ahead.  The loop exists twice: slices that start on a 16-byte
-  // boundary (all shapes where K divides the block nicely) take plain 128-bit loads.
+  // requested one trip ahead (two trips per iteration, so the two register sets just swap roles).
+  // The loop exists twice: slices that start on a 16-byte boundary (all shapes where K divides the
+  // block nicely) take plain 128-bit loads.
   uint32_t groups = sz >> 9;  // full groups still to do
   // keep the trip count and the shared-memory bases in registers: under the kernel's register
   // cap the compiler would otherwise re-derive them from the slice geometry and %warpid every trip
@@ -512,41 +652,31 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   auto full_groups = [&](auto aligned_tag) {
     constexpr bool kAligned = decltype(aligned_tag)::value;
     const uint8_t* p = sp + lane * 16;  // this lane's 16 symbols of the next group
-    uint4 vnext = make_uint4(0, 0, 0, 0);
-    if (groups) vnext = kAligned ? *reinterpret_cast<const uint4*>(p) : load16(p, 0, 16, false, lim);
-    while (groups) {
-      const uint4 v = vnext;
-      p += 512;
-      --groups;
-      if (groups) vnext = kAligned ? *reinterpret_cast<const uint4*>(p) : load16(p, 0, 16, false, lim);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t c01[4], l01[4], c23[4], l23[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        quad_code<true>(entry(w[j], 0), entry(w[j], 1), entry(w[j], 2), entry(w[j], 3), c01[j], l01[j], c23[j],
-                        l23[j]);
-      encode16(c01, l01, c23, l23);
+    auto load = [&](const uint8_t* q) {
+      return kAligned ? ldg128<HUF_L2HINT ? 2 : 0>(reinterpret_cast<const uint4*>(q)) : load16(q, 0, 16, false, lim);
+    };
+    uint4 va = make_uint4(0, 0, 0, 0), vb = va;
+    if (groups) va = load(p);
+    while (groups >= 2) {
+      vb = load(p + 512);
+      trip(va, std::true_type{}, 16);
+      if (groups > 2) va = load(p + 1024);
+      trip(vb, std::true_type{}, 16);
+      p += 1024;
+      groups -= 2;
     }
+    if (groups) trip(va, std::true_type{}, 16);
   };
   if (aligned) full_groups(std::true_type{});
   else full_groups(std::false_type{});
-  // the slice's last, partial group: symbols past its end contribute no bits
+  // the slice's last, partial group
   if (sz & 511u) {
     const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
-    const uint4 v = load16(sp, off, valid, aligned, lim);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t c01[4], l01[4], c23[4], l23[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t e[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) e[i] = (uint32_t)(4 * j + i) < valid ? entry(w[j], i) : 0u;
-      quad_code<true>(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
-    }
-    encode16(c01, l01, c23, l23);
+    trip(load16(sp, off, valid, aligned, lim), std::false_type{}, valid);
   }
   __syncwarp();
   *overflow = over;
+  if (!kPiece && __any_sync(0xffffffffu, (flag & 0x1f000u) != 0)) return ~0ull;  // a symbol without a code
   return bitpos;
 }
 
@@ -572,7 +702,7 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
     uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
     if (lane == 0) hi = carry;
     carry = __shfl_sync(0xffffffffu, lo, 31);
-    *out = __funnelshift_lc(lo, hi, sh);
+    stg32<HUF_L2HINT ? 2 : 0>(out, __funnelshift_lc(lo, hi, sh));
     out -= 32;
     sa += 128;
   }
@@ -849,7 +979,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
   // workers: histogram of block `blk` into sm.hist[slot]
   // (the union is all-zero on entry and left all-zero)
   auto histogram_block = [&](uint32_t blk, int slot) {
-    bins_accumulate(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
+    bins_accumulate<HUF_L2HINT ? 1 : 0>(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
     worker_sync();
     if (tid < 256) sm.hist[slot][tid] = bins_reduce_clear(sm.u.bins, tid);  // one thread per bin
   };
@@ -946,18 +1076,22 @@ struct DecBlockInfo {
 };
 
 // Decode table over the next BITS bits of the stream, up to MAXSYM symbols per entry
-// (generalises Decoder2x, codec/huffman.cpp:642-704).
+// (generalises Decoder1x / Decoder2x, codec/huffman.cpp:594-704).
 //   entry: byte0..2 = symbols, bits 24..27 = stream bits consumed, bits 30..31 = symbol count.
-//   BITS = 12, MAXSYM = 2: exactly the reference's two-symbol table (pair iff l1+l2 <= 12, :653).
-//   BITS = 11, MAXSYM = 3: what the decode kernel uses: three symbols per lookup cut the
-//     lookups, 8 KiB instead of 16 KiB per block keeps more stream groups resident.  A 12-bit
-//     code cannot be resolved by 11 bits, but 12-bit codes come in sibling pairs that share
-//     their first 11 bits (the code is complete), so such an entry holds both candidates
-//     (byte0 for next bit 0, byte1 for next bit 1), one symbol, 12 bits consumed -- and
-//     "12 bits consumed" is the marker, since every other entry of this table consumes <= 11.
+//   BITS = 12, MAXSYM = 2: exactly the reference's two-symbol table (pair iff l1+l2 <= 12, :653);
+//   BITS = 12, MAXSYM = 1: the reference's Decoder1x.  Both are only dumped for parity tests.
+//   BITS = 11, MAXSYM = 3, EXT: what the decode kernel uses: three symbols per lookup cut the
+//     lookups, ~8.5 KiB instead of 16 KiB per block keeps more stream groups resident.  11 bits
+//     cannot resolve a 12-bit code; the canonical code puts the 12-bit codes last, i.e. they own
+//     the prefixes p11 >= P (P = first 12-bit code >> 1), and behind the 11-bit part the table
+//     continues 12-bit-granular: entry P + j holds the j-th 12-bit code.  With p11 / p12 = the
+//     window's first 11 / 12 bits the lookup index is max(p11, p12 - P): for p11 < P the first
+//     wins (p12 - P = p11 + (p11 - P) + bit <= p11), for p11 >= P the second (>= p11), and
+//     p12 - P = P + (p12 - 2P) -- no branch, no fix-up after the load.  A complete code with
+//     n12 12-bit codes has P = 2048 - n12/2, so the table has 2048 + n12/2 <= 2176 entries.
 // L1 (u8 per entry: the first code's own length, 15 = none) is scratch that may be reused
 // afterwards; the first symbol sits in byte 0 of T from the first pass on and never changes.
-template <int BITS, int MAXSYM>
+template <int BITS, int MAXSYM, bool EXT = false>
 __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, uint8_t* L1,
                                     int tid, int nthreads) {
   constexpr int N = 1 << BITS;
@@ -973,12 +1107,10 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
       L1[e] = (uint8_t)l;
     } else {
       L1[e] = 15;  // never fits behind another symbol
-      uint32_t ent = (12u << 24) | (1u << 30);  // sibling pair of 12-bit codes (or a malformed table)
-      if (BITS == kMaxCodeLen - 1 && v < bi->code_end[kMaxCodeLen]) {
-        const uint32_t idx = bi->first_idx[kMaxCodeLen] + (v - bi->code_end[kMaxCodeLen - 1]);
-        ent |= (idx < bi->num_syms ? syms[idx] : 0u) | ((idx + 1 < bi->num_syms ? syms[idx + 1] : 0u) << 8);
-      }
-      T[e] = ent;
+      // no code of at most BITS bits starts here: a malformed (incomplete) table, or -- EXT --
+      // the prefix of 12-bit codes, which the extension below resolves.  One symbol, 12 bits:
+      // whatever reaches such an entry makes progress.
+      T[e] = MAXSYM == 1 ? 0u : (12u << 24) | (1u << 30);
     }
   }
   __syncthreads();
@@ -998,10 +1130,20 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
     T[e] = out | (nb << 24) | (n << 30);
   }
   __syncthreads();
+  if (EXT) {  // the 12-bit codes, one entry each, from index P on (over the dead 11-bit entries)
+    const uint32_t v12 = bi->code_end[kMaxCodeLen - 1];  // first 12-bit code, left-aligned
+    const uint32_t P = v12 >> 1;
+    const uint32_t n12 = bi->code_end[kMaxCodeLen] - v12;
+    for (uint32_t j = tid; j < n12; j += nthreads) {
+      const uint32_t idx = bi->first_idx[kMaxCodeLen] + j;
+      T[P + j] = (idx < bi->num_syms ? syms[idx] : 0u) | (12u << 24) | (1u << 30);
+    }
+    __syncthreads();
+  }
 }
 
-constexpr int kDecBits = 11;  // the sibling-pair entries need exactly one unresolved bit
-constexpr int kDecEntries = 1 << kDecBits;
+constexpr int kDecBits = 11;
+constexpr int kDecEntries = (1 << kDecBits) + 128;  // 11-bit part + one entry per 12-bit code beyond the first 2048 - P (at most 256 of them)
 #ifndef HUF_DEC_LOOKUPS
 #define HUF_DEC_LOOKUPS 10
 #endif
@@ -1046,6 +1188,10 @@ __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int 
   }
   if (nsyms > 256) return;
   if (raw_size != 0 && nsyms == 0) return;
+  // The codes must tile the 12-bit code space exactly (Kraft sum == 1): every Huffman code does,
+  // LimitCodeLengths keeps it so (:297-327), a lone symbol has the empty code (4096 >> 0).  An
+  // over- or under-subscribed length table is corrupt; the decode table relies on completeness.
+  if (nsyms != 0 && code != (1u << kMaxCodeLen)) return;
   bi->num_syms = nsyms;
   bi->syms_off = pos;
   bi->ends_off = pos + nsyms;
@@ -1129,7 +1275,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   for (int lb = 0; lb < bpc; ++lb) {
     const DecBlockInfo* bi = &infos[lb];
     if (b0 + lb < n_blocks && bi->ok && bi->raw_size != 0) {
-      build_dtable<kDecBits, 3>(bi, bi->syms, tables + (size_t)lb * kDecEntries,
+      build_dtable<kDecBits, 3, true>(bi, bi->syms, tables + (size_t)lb * kDecEntries,
                                 region + (size_t)lb * kDecEntries, tid, nthreads);
     }
   }
@@ -1179,12 +1325,14 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
 
   // shared-space addresses, kept in registers
   const uint32_t t_addr = smem_u32(tables + (size_t)(lb < bpc ? lb : 0) * kDecEntries);
+  // base of the 12-bit-granular view: entry (p12 - P); inactive lanes look at entry max(p11, p12)
+  const uint32_t t12_addr = t_addr - 4u * (active ? (bi->code_end[kMaxCodeLen - 1] >> 1) : 0u);
   const uint32_t col = smem_u32(region) + (uint32_t)warp * (16 * 32 * 4) + 4u * (uint32_t)lane;  // word i at col + (i & 15) * 128
   // output staging ring: word j (4 symbols) of this lane at row + (j & 15) * 128 -- lane-private bank
   const uint32_t row = smem_u32(region) + (uint32_t)nwarps * (16 * 32 * 4) + (uint32_t)warp * (32 * kDecRow) + 4u * (uint32_t)lane;
   // make the three addresses opaque so that they stay in registers instead of being recomputed
   // from tid / %ctaid inside the lookup loop
-  asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
+  asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(t12_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
 
   // prime: stage two 32-byte sectors (the whole 16-word ring) and keep the next one in registers.
   // Each top-up takes a full sector, so the kernel does not depend on L1 to serve the other half
@@ -1237,16 +1385,16 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     for (int it = 0; it < kDecLookups; ++it) {
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
       const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
-      uint32_t e = lds_u32_ro(entry_addr(t_addr, win >> (32 - kDecBits)));
+      // index max(p11, p12 - P), formed on the byte addresses (see build_dtable)
+      // (signed max: t12_addr = t_addr - 4P may lie below zero as a shared-window offset)
+      uint32_t e = lds_u32_ro((uint32_t)max((int)entry_addr(t_addr, win >> (32 - kDecBits)),
+                                            (int)entry_addr(t12_addr, win >> (31 - kDecBits))));
       if (decltype(checked)::value && acc >= end_acc) e = 0;
       const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (position in the ring word being filled)
       const uint32_t old = acc;
       acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
       // everything below hangs off that chain
-      uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
-      // rare: a 12-bit code ("12 bits consumed" marks it): the next bit picks one of the two siblings
-      if (__builtin_expect((e & (15u << 24)) == (12u << 24), 0))
-        v = ((win & (1u << (31 - kDecBits))) ? (e >> 8) : e) & 0xffu;
+      const uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
       ob |= v << sh;
       if ((acc ^ old) & 0x100u) {  // the write position crossed a multiple of 4: one ring word is complete
         sts_u32(row + wofs, ob);
