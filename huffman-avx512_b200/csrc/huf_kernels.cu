@@ -66,6 +66,9 @@ __device__ __forceinline__ uint32_t bins_reduce_clear(uint32_t* bins, int t) {
 #ifndef HUF_L2HINT
 #define HUF_L2HINT 0
 #endif
+#ifndef HUF_PREFETCH_L2
+#define HUF_PREFETCH_L2 0
+#endif
 __device__ __forceinline__ unsigned long long l2_policy_last() {
   unsigned long long p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -219,6 +222,8 @@ struct CompSmem {
   uint32_t region_end[kMaxK];  // cumulative end offsets relative to the payload start (:772-786)
   uint32_t bad;
   uint32_t blk_new, blk_new2;  // block indices just drawn from the launch's counter
+  uint32_t ticket;             // next stream of the current block to be encoded (staged mode)
+  unsigned long long placed[kMaxK];  // mbarriers: [s] completes once per staged block, when region_end[s] is known
 };
 
 __device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) {  // shift >= 32 gives 0
@@ -512,57 +517,31 @@ __device__ __forceinline__ void stage_put64_start(uint32_t stream_base, uint32_t
   red_or_shared_off<8>(a, __funnelshift_r(0u, lo, pos));  // 0 for r == 0
 }
 
-// One trip (16 symbols per lane) the general way: entries of HufTable::enc (code | len << 16),
-// pair and quad codes right-aligned, 64-bit puts when every quad has at most 32 bits, else quad by
-// quad.  Any code lengths.  Kept out of line: the staged encoder below takes it only when a quad
-// is longer than 32 bits.
-// Takes and returns the running bit position with the overflow flag in bit 31 (by value: a
-// reference into the caller's frame would pin those variables to local memory).
-__device__ __noinline__ uint32_t encode_trip_general(uint32_t enc_addr, uint32_t sb, uint32_t w0, uint32_t w1,
-                                                     uint32_t w2, uint32_t w3, uint32_t valid, uint32_t state) {
-  uint32_t bitpos = state & 0x7fffffffu;
-  bool over = (state >> 31) != 0;
+// The puts of one lane's 16 symbols the general way: entries of HufTable::enc (code | len << 16),
+// pair and quad codes right-aligned, one put per quad (two for a quad longer than 32 bits).  Any
+// code lengths.  Out of line: the staged encoder below takes it, lane by lane, only when one of
+// the lane's quads is longer than 32 bits.  pos: stream bit position of the lane's first code.
+__device__ __noinline__ void put16_general(uint32_t enc_addr, uint32_t sb, uint32_t w0, uint32_t w1, uint32_t w2,
+                                           uint32_t w3, uint32_t valid, uint32_t pos) {
   const uint32_t w[4] = {w0, w1, w2, w3};
-  uint32_t c01[4], l01[4], c23[4], l23[4], lq[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint32_t e[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
       e[i] = (uint32_t)(4 * j + i) < valid ? lds_u32_ro(entry_addr(enc_addr, byte_of(w[j], i))) : 0u;
-    quad_code<true>(e[0], e[1], e[2], e[3], c01[j], l01[j], c23[j], l23[j]);
-    lq[j] = l01[j] + l23[j];
-  }
-  const uint32_t lane_len = (lq[0] + lq[1]) + (lq[2] + lq[3]);
-  const uint32_t incl = warp_incl_scan(lane_len);
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  // a symbol without a code makes `total` huge and lands here as an overflow, too
-  if (bitpos + total > kStageLimitBits) over = true;
-  const uint32_t longest = max(max(lq[0], lq[1]), max(lq[2], lq[3]));
-  uint32_t pos = bitpos + (incl - lane_len);
-  if (!over && longest <= 32u) {
-#pragma unroll
-    for (int h = 0; h < 4; h += 2) {
-      const uint32_t qa = (c01[h] << l23[h]) | c23[h];
-      const uint32_t qb = (c01[h + 1] << l23[h + 1]) | c23[h + 1];
-      pos += lq[h] + lq[h + 1];
-      stage_put64_end(sb, pos, __funnelshift_lc(qa, 0u, lq[h + 1]), shl_c(qa, lq[h + 1]) | qb);
+      if (e[i] == kEncInvalid) e[i] = 0;  // no bits, as in enc2 (the stream is flagged by its entry sums)
     }
-  } else if (!over) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (lq[j] <= 32) {
-        stage_put(sb, pos, (c01[j] << l23[j]) | c23[j], lq[j]);
-      } else {
-        stage_put(sb, pos, c01[j], l01[j]);
-        stage_put(sb, pos + l01[j], c23[j], l23[j]);
-      }
-      pos += lq[j];
+    uint32_t c01, l01, c23, l23;
+    quad_code<true>(e[0], e[1], e[2], e[3], c01, l01, c23, l23);
+    if (l01 + l23 <= 32) {
+      stage_put(sb, pos, (c01 << l23) | c23, l01 + l23);
+    } else {
+      stage_put(sb, pos, c01, l01);
+      stage_put(sb, pos + l01, c23, l23);
     }
+    pos += l01 + l23;
   }
-  bitpos += total;
-  if (bitpos > 0x7fffffffu) bitpos = 0x7fffffffu;  // (over is set long before)
-  return bitpos | (over ? 0x80000000u : 0u);
 }
 
 // Staged mode, step 1: encode the whole stream into the warp's linear staging buffer (zeroed by
@@ -582,9 +561,9 @@ __device__ __noinline__ uint32_t encode_trip_general(uint32_t enc_addr, uint32_t
 //     quad has at most 32 bits;
 //   * two quads make a top-aligned 64-bit value that goes to the lane's scanned bit position with
 //     three red.shared.or (stage_put64_start).
-// A trip in which some lane has a quad longer than 32 bits (a warp vote) is redone the general
-// way (encode_trip_general); so are streams of symbols without a code, which the marker bit of
-// their enc2 entry exposes in the entry sums.
+// A lane with a quad longer than 32 bits (rare) does its puts the general way (put16_general);
+// lengths and positions come from the entry sums either way.  A symbol without a code has an
+// enc2 entry of no bits and a marker bit that survives the sums: such a stream is reported.
 template <bool kPiece = false>
 __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr, uint32_t stage_base,
                                                                const uint8_t* sp, uint32_t sz, bool* overflow,
@@ -617,24 +596,21 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
     flag |= T;
     // quad longer than 32 bits <=> bit 6 of (its length + 31); lengths sit in bits 0..5 of S
     const uint32_t chk = ((S[0] + 31u) | (S[1] + 31u)) | ((S[2] + 31u) | (S[3] + 31u));
-    if (__any_sync(0xffffffffu, (chk & 0x40u) != 0)) {
-      const uint32_t st = encode_trip_general(enc_addr, sb, w[0], w[1], w[2], w[3], kFull ? 16u : valid,
-                                              bitpos | (over ? 0x80000000u : 0u));
-      bitpos = st & 0x7fffffffu;
-      over = (st >> 31) != 0;
-      return;
-    }
     const uint32_t lane_len = T & 0xffu;
     const uint32_t incl = warp_incl_scan(lane_len);
     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
     if (bitpos + total > kStageLimitBits) over = true;  // the same in every lane
     if (!over) {
       uint32_t pos = bitpos + (incl - lane_len);
+      if (!(chk & 0x40u)) {
 #pragma unroll
-      for (int h = 0; h < 4; h += 2) {
-        const uint32_t a = S[h] & 0x3fu;  // 0..32: clamping shifts
-        stage_put64_start(sb, pos, Q[h] | __funnelshift_rc(Q[h + 1], 0u, a), __funnelshift_rc(0u, Q[h + 1], a));
-        if (h == 0) pos += sA & 0x7fu;
+        for (int h = 0; h < 4; h += 2) {
+          const uint32_t a = S[h] & 0x3fu;  // 0..32: clamping shifts
+          stage_put64_start(sb, pos, Q[h] | __funnelshift_rc(Q[h + 1], 0u, a), __funnelshift_rc(0u, Q[h + 1], a));
+          if (h == 0) pos += sA & 0x7fu;
+        }
+      } else {
+        put16_general(enc_addr, sb, w[0], w[1], w[2], w[3], kFull ? 16u : valid, pos);
       }
     }
     bitpos += total;
@@ -681,7 +657,10 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
 }
 
 // Staged mode, step 2: the staged stream words go out as aligned 128-byte rows below e_off
-// (same alignment algebra as encode_stream_warp); the buffer is left zeroed.
+// (same alignment algebra as encode_stream_warp): output word m = top half of
+// (W[m-1] : W[m]) << 8r with W[-1] = 0 (the zero word in front of the stream) and W[m] = 0 from
+// the stream's end on.  A lane reads both words itself (two conflict-free loads; no shuffles),
+// and the buffer is zeroed afterwards with 128-bit stores.
 __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long long bits, uint8_t* dst,
                                             uint32_t e_off, uint32_t region) {
   const int lane = lane_id();
@@ -693,34 +672,37 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
   const uint32_t wtot = (uint32_t)((bits + 31) >> 5);
   uint32_t* out = reinterpret_cast<uint32_t*>(dst + e_al) - lane;  // this lane's word of the current row
   uint32_t sa = stage_base + 4u * (uint32_t)(kStageFront + lane);  // stream word `lane`
-  uint32_t carry = 0;
-  uint32_t m0 = 0;
-  // full rows: 32 data words each, no predicates
-  for (; m0 + 32 <= wtot; m0 += 32) {
-    const uint32_t lo = lds_u32(sa);
-    sts_u32(sa, 0);
-    uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
-    if (lane == 0) hi = carry;
-    carry = __shfl_sync(0xffffffffu, lo, 31);
-    stg32<HUF_L2HINT ? 2 : 0>(out, __funnelshift_lc(lo, hi, sh));
+  uint32_t rows = wtot >> 5;  // rows of 32 data words: no predicates
+  const uint32_t m_tail = rows << 5;
+  for (; rows >= 2; rows -= 2) {
+    const uint32_t lo0 = lds_u32(sa), hi0 = lds_u32(sa - 4u);
+    const uint32_t lo1 = lds_u32(sa + 128u), hi1 = lds_u32(sa + 124u);
+    stg32<HUF_L2HINT ? 2 : 0>(out, __funnelshift_lc(lo0, hi0, sh));
+    stg32<HUF_L2HINT ? 2 : 0>(out - 32, __funnelshift_lc(lo1, hi1, sh));
+    out -= 64;
+    sa += 256;
+  }
+  if (rows) {
+    const uint32_t lo0 = lds_u32(sa), hi0 = lds_u32(sa - 4u);
+    stg32<HUF_L2HINT ? 2 : 0>(out, __funnelshift_lc(lo0, hi0, sh));
     out -= 32;
     sa += 128;
   }
   // the rest: remaining data words, the partial word, padding and the zero slop
-  for (; m0 <= m_last; m0 += 32) {
+  for (uint32_t m0 = m_tail; m0 <= m_last; m0 += 32) {
     const uint32_t m = m0 + lane;
-    uint32_t lo = 0;
-    if (m < wtot) {
-      lo = lds_u32(sa);
-      sts_u32(sa, 0);
-    }
-    uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
-    if (lane == 0) hi = carry;
-    carry = __shfl_sync(0xffffffffu, lo, 31);
+    const uint32_t lo = m < wtot ? lds_u32(sa) : 0u;
+    const uint32_t hi = m <= wtot ? lds_u32(sa - 4u) : 0u;
     if (m <= m_last) *out = __funnelshift_lc(lo, hi, sh);
     out -= 32;
     sa += 128;
   }
+  __syncwarp();
+  // zero what the stream used: 16-byte stores from the buffer's start (two words before the
+  // stream) up to the 512-byte line that holds its last word -- never past the warp's buffer
+  static_assert(kStageWords % 128 == 0 && kStageFront == 2, "zeroing rows cover whole 512-byte lines of the buffer");
+  for (uint32_t i = 4u * (uint32_t)lane; i < wtot + kStageFront; i += 128u)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(stage_base + 4u * i), "r"(0u) : "memory");
   __syncwarp();
 }
 
@@ -798,14 +780,39 @@ __device__ inline void encode_long_stream_warp(uint32_t enc_addr, uint32_t stage
 // Worker-only barrier (named barrier 1): the table-builder warp never takes part in it.
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory"); }
 
+// mbarrier (shared memory, CTA scope): one arrival completes a phase; a waiter is suspended by
+// the hardware until the phase of the given parity is complete -- no polling loop that would
+// compete for issue slots with the warps it waits for.
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {  // release: what was written before is visible to the waiter
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {  // acquire
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 // Everything the workers do for one block once its table is in `tab`: header, streams, sizes.
 // kLongSlices = false: every slice has at most kStageSlice symbols (decided at launch from the
 // geometry), so only the staged mode and its per-stream fallback are compiled in -- the kernel of
 // the common shapes carries no code for long streams.
+// Returns whether the block went through the staged mode (the caller counts those blocks: the
+// count's parity is the phase the placement barriers are in).
 template <bool kLongSlices>
-__device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, const uint8_t* raw, uint64_t n,
+__device__ inline bool encode_block_workers(CompSmem& sm, const HufTable& tab, const uint8_t* raw, uint64_t n,
                                             const uint8_t* src, uint32_t bn, uint32_t block_size, int K,
-                                            uint8_t* dst, uint32_t* comp_size_out, uint32_t* status) {
+                                            uint8_t* dst, uint32_t* comp_size_out, uint32_t* status,
+                                            uint32_t staged_iter) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -850,52 +857,50 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
     for (uint32_t a = hdr_total; a & 3u; ++a) dst[a] = 0;  // slop bytes sharing a word with the header
 
   if (staged) {
-    // ---- staged mode: rounds of kCompWarps streams; encode into shared memory, then place.
-    // One barrier per round: after it every warp derives the round's region ends itself from
-    // the published bit totals (:772-786).  The loop always runs all rounds (a block flagged
-    // bad only skips its global writes), so the barriers stay uniform.
-    uint32_t run_end = 0;  // end offset of the last placed region, identical in all threads
-    for (int s0 = 0; s0 < K; s0 += kCompWarps) {
-      const int s = s0 + warp;
-      uint32_t st = 0, sz = 0;
+    // ---- staged mode: a warp draws the next stream of the block (a ticket), encodes it into its
+    // staging buffer -- which gives the stream's size -- and places it behind its predecessor:
+    // region ends are cumulative (:772-786), so stream s waits until the end of stream s-1 is
+    // published (mbarrier placed[s-1]), adds its own size, publishes, and copies its words out.
+    // Tickets go out in stream order, so a predecessor has always started earlier and nobody waits
+    // for a warp that waits for it; there is no barrier inside the block.  All K tickets are
+    // always drawn (a block flagged bad only skips its global writes): every placement barrier
+    // completes exactly once per staged block.
+    const uint32_t parity = staged_iter & 1u;
+    const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
+    for (;;) {
+      uint32_t s = 0;
+      if (lane == 0) s = atomicAdd(&sm.ticket, 1u);
+      s = __shfl_sync(0xffffffffu, s, 0);
+      if (s >= (uint32_t)K) break;
+      uint32_t st, sz;
+      geom((int)s, st, sz);
       bool over = false;
-      unsigned long long bits = 0;
-      const uint32_t stage_base = smem_u32(&sm.u.stage[warp][0]);
-      if (s < K) {
-        geom(s, st, sz);
-        bits = encode_stream_staged_warp(smem_u32(tab.enc), stage_base, src + st, sz, &over, raw + n);
-        if (bits > 12ull * sz) atomicOr(&sm.bad, 1u);  // a symbol without a code
-        if (lane == 0) sm.stream_bits[s] = bits;
+      const unsigned long long bits = encode_stream_staged_warp(smem_u32(tab.enc), stage_base, src + st, sz, &over, raw + n);
+      if (bits > 12ull * sz && lane == 0) atomicOr(&sm.bad, 1u);  // a symbol without a code
+      const uint32_t my_region = (uint32_t)((bits + 7) >> 3) + kSlop;
+      uint32_t prev_end = 0;
+      if (s != 0) {
+        mbar_wait(smem_u32(&sm.placed[s - 1]), parity);
+        prev_end = *reinterpret_cast<volatile uint32_t*>(&sm.region_end[s - 1]);
       }
-      worker_sync();
-      const bool bad_now = sm.bad != 0;  // covers every stream up to this round
-      // region sizes of the round's streams: lane t of every warp takes stream s0 + t, a
-      // kCompWarps-wide shuffle scan gives the running ends
-      uint32_t reg = 0;
-      if (lane < kCompWarps && s0 + lane < K) reg = (uint32_t)((sm.stream_bits[s0 + lane] + 7) >> 3) + kSlop;
-      uint32_t incl = reg;
-#pragma unroll
-      for (int d = 1; d < kCompWarps; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
+      const uint32_t my_end = prev_end + my_region;
+      if (lane == 0) {
+        *reinterpret_cast<volatile uint32_t*>(&sm.region_end[s]) = my_end;
+        mbar_arrive(smem_u32(&sm.placed[s]));
       }
-      const uint32_t my_region = __shfl_sync(0xffffffffu, reg, warp);
-      const uint32_t my_end = run_end + __shfl_sync(0xffffffffu, incl, warp);
-      run_end += __shfl_sync(0xffffffffu, incl, kCompWarps - 1);
-      if (s < K) {
-        if (lane == 0) sm.region_end[s] = my_end;
-        if (!bad_now) {
-          const uint32_t e_off = hdr_total + my_end;
-          if (!over) {
-            copy_stream_out_warp(stage_base, bits, dst, e_off, my_region);
-          } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
-            for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
-            __syncwarp();
-            encode_stream_warp(tab.enc, stage_base, src + st, sz, bits, dst, e_off, my_region, raw + n);
-          }
-        } else {  // leave the staging buffer clean for the next block
+      const bool bad_now = *reinterpret_cast<volatile uint32_t*>(&sm.bad) != 0;  // covers every stream up to this one
+      if (!bad_now) {
+        const uint32_t e_off = hdr_total + my_end;
+        if (!over) {
+          copy_stream_out_warp(stage_base, bits, dst, e_off, my_region);
+        } else {  // rare: more than 10 bits/symbol in this slice -> ring path, now that e_off is known
           for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
+          __syncwarp();
+          encode_stream_warp(tab.enc, stage_base, src + st, sz, bits, dst, e_off, my_region, raw + n);
         }
+      } else {  // leave the staging buffer clean for the next block
+        for (int j = lane; j < kStageWords; j += 32) sts_u32(stage_base + 4u * j, 0);
+        __syncwarp();
       }
     }
     worker_sync();
@@ -945,6 +950,7 @@ __device__ inline void encode_block_workers(CompSmem& sm, const HufTable& tab, c
     }
     if (tid == 0) *comp_size_out = hdr_total + sm.region_end[K - 1];
   }
+  return staged;
 }
 
 // Work counters of the compress launches.  Every launch takes the next pair round-robin; a pair
@@ -979,7 +985,11 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
   // workers: histogram of block `blk` into sm.hist[slot]
   // (the union is all-zero on entry and left all-zero)
   auto histogram_block = [&](uint32_t blk, int slot) {
+#ifdef HUF_EXP_ALIAS  // tuning probe: every block reads the same few blocks, so the input stays in L2
+    bins_accumulate<0>(sm.u.bins, raw + (uint64_t)(blk % HUF_EXP_ALIAS) * block_size, block_len(blk), tid, kWorkThreads);
+#else
     bins_accumulate<HUF_L2HINT ? 1 : 0>(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
+#endif
     worker_sync();
     if (tid < 256) sm.hist[slot][tid] = bins_reduce_clear(sm.u.bins, tid);  // one thread per bin
   };
@@ -992,6 +1002,8 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
     uint4* z = reinterpret_cast<uint4*>(&sm.u);
     for (int i = tid; i < (int)(sizeof(sm.u) / 16); i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
+  if (tid < kMaxK) mbar_init(smem_u32(&sm.placed[tid]), 1);  // made visible by the __syncthreads below
+  uint32_t staged_iter = 0;  // staged blocks this CTA has encoded (workers only; the same in each)
   // Blocks are handed out dynamically (one atomic per block on a per-launch counter): the CTAs
   // that share an SM do not progress at the same rate, and with a static split the SM would
   // run the last quarter of the kernel with one or two CTAs left.  A CTA always knows its
@@ -1024,6 +1036,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
       if (!builder) {
         if (tid == 0) {
           sm.bad = 0;
+          sm.ticket = 0;
           sm.blk_new = atomicAdd(&counters[0], 1u);  // the block after the next one
         }
         if (have_next) histogram_block(nxt, cur ^ 1);
@@ -1037,9 +1050,23 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
         if (!own_tables && check_presence) {  // every symbol of the block needs a code in the supplied table
           if (tid < 256 && sm.hist[cur][tid] != 0 && sm.tab[cur].enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
         }
+#ifdef HUF_EXP_ALIAS
+        const uint64_t boff = (uint64_t)(b % HUF_EXP_ALIAS) * block_size;
+#else
         const uint64_t boff = (uint64_t)b * block_size;
-        encode_block_workers<kLongSlices>(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
-                             out + (uint64_t)b * slot_stride, comp_sizes + b, status);
+#endif
+#if HUF_PREFETCH_L2
+        {  // the block was read for its histogram a whole block period ago and has left the L2 since:
+           // ask for it again, ahead of the encoder's loads (one 128-byte line per request)
+          const uint8_t* pb = raw + boff;
+          const uint32_t bl = block_len(b);
+          for (uint32_t o = (uint32_t)tid * 128u; o < bl; o += kWorkThreads * 128u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
+        }
+#endif
+        if (encode_block_workers<kLongSlices>(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
+                                              out + (uint64_t)b * slot_stride, comp_sizes + b, status, staged_iter))
+          ++staged_iter;
       }
       __syncthreads();
       b = nxt;
