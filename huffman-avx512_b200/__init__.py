@@ -11,11 +11,11 @@ but every compute call raises `HufError` when no CUDA device is usable.
 """
 from .binding import (HufError, lib, lib_path, load, HuffmanCompressorB200, MakeHistogram, compress,
                       decompress, compress_with_table, compress_blocks, decompress_blocks, make_table,
-                      decode_table, compress_bound, slot_stride, blocks_count, launch_count, ABI_SYMBOLS)
+                      decode_table, decode_table1x, compress_bound, slot_stride, blocks_count, launch_count, ABI_SYMBOLS)
 from .device import BlockCodec
 from . import sharded
 
 __all__ = ["HufError", "lib", "lib_path", "load", "HuffmanCompressorB200", "MakeHistogram", "compress",
            "decompress", "compress_with_table", "compress_blocks", "decompress_blocks", "make_table",
-           "decode_table", "compress_bound", "slot_stride", "blocks_count", "launch_count", "BlockCodec",
+           "decode_table", "decode_table1x", "compress_bound", "slot_stride", "blocks_count", "launch_count", "BlockCodec",
            "sharded", "ABI_SYMBOLS"]

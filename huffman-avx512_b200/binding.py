@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     ("hufb200_histogram_dev", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     ("hufb200_make_table", C.c_int, [u32p, u16p, u8p, C.POINTER(C.c_int), u32p, u16p, u16p]),
     ("hufb200_decode_table", C.c_int, [u16p, C.c_void_p, C.c_int, u8p]),
+    ("hufb200_decode_table1x", C.c_int, [u16p, C.c_void_p, C.c_int, u8p]),
     ("hufb200_compress_bound", C.c_size_t, [C.c_size_t, C.c_int]),
     ("hufb200_compress", C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, szp]),
     ("hufb200_decompress", C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, szp]),
@@ -193,6 +194,15 @@ def decode_table(len_count, sorted_syms):
     out = np.zeros(4096 * 4, dtype=np.uint8)
     check(load().hufb200_decode_table(lc.ctypes.data_as(u16p), _vp(sy), sy.size, out.ctypes.data_as(u8p)))
     return out.reshape(4096, 4)
+
+
+def decode_table1x(len_count, sorted_syms):
+    """Decoder1x table (codec/huffman.cpp:594-632) from the same builder: (4096, 2) u8 {code_len, sym}."""
+    lc = np.ascontiguousarray(np.asarray(len_count, dtype=np.uint16))
+    sy = _np_u8(sorted_syms)
+    out = np.zeros(4096 * 2, dtype=np.uint8)
+    check(load().hufb200_decode_table1x(lc.ctypes.data_as(u16p), _vp(sy), sy.size, out.ctypes.data_as(u8p)))
+    return out.reshape(4096, 2)
 
 
 def compress_blocks(k, block_size, raw):

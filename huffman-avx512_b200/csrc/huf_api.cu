@@ -314,8 +314,21 @@ int hufb200_make_table(const uint32_t hist[256], uint16_t len_count[13], uint8_t
   return HUFB200_OK;
 }
 
+namespace {
+int decode_table_dump(const uint16_t len_count[13], const uint8_t* sorted_syms, int num_syms, int one_symbol,
+                      uint8_t* out);
+}
 int hufb200_decode_table(const uint16_t len_count[13], const uint8_t* sorted_syms, int num_syms,
                          uint8_t out[4096 * 4]) {
+  return decode_table_dump(len_count, sorted_syms, num_syms, 0, out);
+}
+int hufb200_decode_table1x(const uint16_t len_count[13], const uint8_t* sorted_syms, int num_syms,
+                           uint8_t out[4096 * 2]) {
+  return decode_table_dump(len_count, sorted_syms, num_syms, 1, out);
+}
+namespace {
+int decode_table_dump(const uint16_t len_count[13], const uint8_t* sorted_syms, int num_syms, int one_symbol,
+                      uint8_t* out) {
   if (!len_count || !out || num_syms < 0 || num_syms > 256 || (!sorted_syms && num_syms))
     return fail(HUFB200_E_INVALID, "bad table arguments");
   Workspace& ws = g_ws;
@@ -325,12 +338,13 @@ int hufb200_decode_table(const uint16_t len_count[13], const uint8_t* sorted_sym
   uint8_t* d_sy = d_lc + 64;
   CU(cudaMemcpyAsync(d_lc, len_count, 13 * sizeof(uint16_t), cudaMemcpyHostToDevice, 0));
   if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, 0));
-  CU(launch_dump_dtable(reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, ws.out.as<uint8_t>(), 0));
+  CU(launch_dump_dtable(reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, one_symbol, ws.out.as<uint8_t>(), 0));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  CU(cudaMemcpyAsync(out, ws.out.p, 4096 * 4, cudaMemcpyDeviceToHost, 0));
+  CU(cudaMemcpyAsync(out, ws.out.p, one_symbol ? 4096 * 2 : 4096 * 4, cudaMemcpyDeviceToHost, 0));
   CU(cudaStreamSynchronize(0));
   return HUFB200_OK;
 }
+}  // namespace
 
 /* -------------------------------------------------------------- single buffer */
 

@@ -1323,6 +1323,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t rd = 0, staged = 0, cidx = 0;
   uint32_t ob = 0;             // pending output symbols (fewer than 4), first symbol in the low byte
   bool bad_lane = false;
+  uint32_t region_bytes = 0, pad_bits = 0;  // for the end-of-stream check
   if (active) {
     const uint8_t* blk = comp + offsets[b];
     uint32_t st, sz;
@@ -1334,11 +1335,21 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       const uint8_t* p = blk + bi->ends_off + 4 * s;
       e_off = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
     }
-    if (e_off > payload) {  // corrupt end offset: produce nothing and read nothing through it
+    // the region in front: ends are cumulative and every region holds at least its 8 slop bytes (:783-786)
+    uint32_t e_prev = 0;
+    if (s != 0) {
+      const uint8_t* p = blk + bi->ends_off + 4 * (s - 1);
+      e_prev = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+    if (e_off > payload || e_prev > e_off || e_off - e_prev < (uint32_t)kSlop) {
+      // corrupt end offsets: produce nothing and read nothing through them
       bad_lane = true;
       sz = 0;
       e_off = 0;
+      e_prev = 0;
     }
+    region_bytes = e_off - e_prev;
+    pad_bits = 0;
     left = sz;
     outp = raw + (uint64_t)b * block_size + st;
     const uintptr_t end_addr = (uintptr_t)(blk + bi->payload_off) + e_off;  // exclusive
@@ -1347,6 +1358,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     lo_lim = (uintptr_t)blk & ~(uintptr_t)31;
     rd = pad >> 2;
     acc = 8 * (pad & 3);
+    pad_bits = 8 * pad;
   }
   if (bad_lane && status) atomicOr(status, 1u);
 
@@ -1502,13 +1514,28 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     if (p < h0) p = h0;
     for (; p < end_pos; ++p) out_al[p] = (uint8_t)lds_u8(row + (((p >> 2) * 128) & kRowWrap) + (p & 3));
   }
+  // A stream of b bits sits in a region of ceil(b / 8) + 8 bytes (:783-786), so the bits this
+  // lane consumed for its symbols must end inside the region's first stream byte: anything else
+  // means a corrupt table, payload or end offset, even if every access stayed inside the block.
+  // Position = 32 * (ring words behind the window) + bits consumed from the window.  The last
+  // lookup may have decoded up to two symbols more than the slice has (from the zero padding
+  // behind the stream; they are not written): each of them accounts for at most 12 bits more.
+  if (active && !bad_lane) {
+    const uint32_t consumed = 32u * (rd - 2u) + (acc & 63u) - pad_bits;
+    const uint32_t extra = left ? (acc >> 6) - end_pos : 0u;  // 0..2 symbols past the slice's end
+    const uint32_t stream_bits_max = 8u * (region_bytes - (uint32_t)kSlop);
+    const bool ok = consumed + 7u >= stream_bits_max && consumed <= stream_bits_max + (uint32_t)kMaxCodeLen * extra &&
+                    extra <= 2u;
+    if (!ok && status) atomicOr(status, 1u);
+  }
 }
 
-// Dumps the reference-format two-symbol table (BITS = 12, 2 symbols) built by the decode
-// kernel's builder: DecodedSym2x {num_bits_decoded, syms[2], num_syms} (:634-640).
+// Dumps the reference-format decode tables (BITS = 12) built by the decode kernel's builder:
+// one_symbol == 0: DecodedSym2x {num_bits_decoded, syms[2], num_syms} (:634-640), 4 bytes per entry;
+// one_symbol != 0: DecodedSym {code_len, sym} of Decoder1x (:588-632), 2 bytes per entry.
 __global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict__ len_count,
                                                      const uint8_t* __restrict__ syms, int num_syms,
-                                                     uint8_t* __restrict__ out) {
+                                                     int one_symbol, uint8_t* __restrict__ out) {
   __shared__ uint32_t T[4096];
   __shared__ uint8_t T1[4096];
   __shared__ DecBlockInfo bi;
@@ -1525,6 +1552,15 @@ __global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict_
   }
   for (int i = threadIdx.x; i < num_syms; i += blockDim.x) sy[i] = syms[i];
   __syncthreads();
+  if (one_symbol) {
+    build_dtable<kMaxCodeLen, 1>(&bi, sy, T, T1, threadIdx.x, blockDim.x);
+    for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
+      const uint32_t v = T[e];  // 0 where no code starts (the reference leaves {0, 0} there)
+      out[2 * e + 0] = (uint8_t)((v >> 24) & 15u);
+      out[2 * e + 1] = (uint8_t)v;
+    }
+    return;
+  }
   build_dtable<kMaxCodeLen, 2>(&bi, sy, T, T1, threadIdx.x, blockDim.x);
   for (int e = threadIdx.x; e < 4096; e += blockDim.x) {
     const uint32_t v = T[e];
@@ -1668,9 +1704,9 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
   return cudaGetLastError();
 }
 
-cudaError_t launch_dump_dtable(const uint16_t* d_len_count, const uint8_t* d_syms, int num_syms, uint8_t* d_out,
-                               cudaStream_t st) {
-  k_dump_dtable<<<1, 256, 0, st>>>(d_len_count, d_syms, num_syms, d_out);
+cudaError_t launch_dump_dtable(const uint16_t* d_len_count, const uint8_t* d_syms, int num_syms, int one_symbol,
+                               uint8_t* d_out, cudaStream_t st) {
+  k_dump_dtable<<<1, 256, 0, st>>>(d_len_count, d_syms, num_syms, one_symbol, d_out);
   return cudaGetLastError();
 }
 

@@ -35,8 +35,8 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
 cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
                               const uint32_t* d_sizes, uint32_t n_blocks, int K, int bpc, uint8_t* d_raw,
                               uint64_t raw_n, uint32_t block_size, uint32_t* d_status, cudaStream_t st);
-cudaError_t launch_dump_dtable(const uint16_t* d_len_count, const uint8_t* d_syms, int num_syms, uint8_t* d_out,
-                               cudaStream_t st);
+cudaError_t launch_dump_dtable(const uint16_t* d_len_count, const uint8_t* d_syms, int num_syms, int one_symbol,
+                               uint8_t* d_out, cudaStream_t st);
 cudaError_t launch_pack(const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes, uint32_t n_blocks,
                         uint8_t* d_packed, unsigned long long* d_offsets, unsigned long long* d_total,
                         cudaStream_t st);

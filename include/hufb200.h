@@ -66,6 +66,10 @@ HUFB200_API int hufb200_make_table(const uint32_t hist[256], uint16_t len_count[
  * {num_bits, sym0, sym1, num_syms} (DecodedSym2x, :634-640).  Runs the decode kernel's builder. */
 HUFB200_API int hufb200_decode_table(const uint16_t len_count[13], const uint8_t* sorted_syms, int num_syms,
                          uint8_t out[4096 * 4]);
+/* One-symbol decode table: Decoder1x, codec/huffman.cpp:594-632.  out = 4096 entries of
+ * {code_len, sym} (DecodedSym, :588-592); entries no code reaches stay {0, 0}.  Same builder. */
+HUFB200_API int hufb200_decode_table1x(const uint16_t len_count[13], const uint8_t* sorted_syms, int num_syms,
+                           uint8_t out[4096 * 2]);
 
 /* ---- single buffer: huffman::CompressMulti<K> / DecompressMulti<K>,
  * codec/huffman.h:9-12, codec/huffman.cpp:738-846 / :892-960 ---- */

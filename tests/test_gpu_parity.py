@@ -110,6 +110,17 @@ def test_decode_table_matches_oracle(huf, oracle):
         assert np.array_equal(got, want)
 
 
+def test_decode_table1x_matches_oracle(huf, oracle):
+    """Decoder1x (codec/huffman.cpp:594-632): {code_len, sym} per 12-bit prefix, from the kernel's builder."""
+    for _, data in ALL_CASES[:10] + extra_cases():
+        if not data:
+            continue
+        cd = oracle.make_coding(oracle.histogram(data))
+        want = oracle.dtable(1, cd["len_count"], cd["sorted_syms"])
+        got = huf.decode_table1x(cd["len_count"], cd["sorted_syms"])
+        assert np.array_equal(got, want)
+
+
 def test_compress_with_table(huf, oracle):
     data = golden("proba02_100k.bin")
     other = biased(50_000, seed=11)
