@@ -20,6 +20,7 @@ ABI_SYMBOLS = [
     ("hufb200_last_error", C.c_char_p, []),
     ("hufb200_device_count", C.c_int, []),
     ("hufb200_launch_count", C.c_uint64, []),
+    ("hufb200_release_workspace", None, []),
     ("hufb200_histogram", C.c_int, [C.c_void_p, C.c_size_t, u32p]),
     ("hufb200_histogram64", C.c_int, [C.c_void_p, C.c_size_t, u64p]),
     ("hufb200_histogram_dev", C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
@@ -147,11 +148,17 @@ def compress(k, raw):
     return out[: n.value].tobytes()
 
 
-def decompress(k, comp):
-    """huffman::DecompressMulti<k> (codec/huffman.h:11-12)."""
+MAX_SINGLE_BUFFER = 1 << 30  # the library's single-buffer limit (32-bit offsets, codec/huffman.cpp:772)
+
+
+def decompress(k, comp, max_raw=MAX_SINGLE_BUFFER):
+    """huffman::DecompressMulti<k> (codec/huffman.h:11-12).  The output is sized from the buffer's
+    untrusted raw_size field, so that is checked against `max_raw` before anything is allocated."""
     a = _np_u8(comp)
     rs = C.c_size_t(0)
     check(load().hufb200_raw_size(_vp(a), a.size, C.byref(rs)))
+    if rs.value > max_raw:
+        raise HufError(E_CORRUPT, f"header claims {rs.value} raw bytes, more than max_raw={max_raw}")
     out = np.empty(max(rs.value, 1), dtype=np.uint8)
     n = C.c_size_t(0)
     check(load().hufb200_decompress(k, _vp(a), a.size, _vp(out), rs.value, C.byref(n)))
@@ -221,9 +228,14 @@ def container_info(container):
     return dict(k=k.value, block_size=bs.value, raw_size=rs.value, n_blocks=nb.value)
 
 
-def decompress_blocks(container):
+def decompress_blocks(container, max_raw=None):
+    """Decodes a block container.  A few kilobytes of header can claim terabytes of raw data (a
+    block of one repeated symbol has no payload bits), so pass `max_raw` when the container is
+    untrusted: the claimed size is checked against it before the output is allocated."""
     a = _np_u8(container)
     info = container_info(a)
+    if max_raw is not None and info["raw_size"] > max_raw:
+        raise HufError(E_CORRUPT, f"container claims {info['raw_size']} raw bytes, more than max_raw={max_raw}")
     out = np.empty(max(info["raw_size"], 1), dtype=np.uint8)
     n = C.c_size_t(0)
     check(load().hufb200_decompress_blocks(_vp(a), a.size, _vp(out), info["raw_size"], C.byref(n)))

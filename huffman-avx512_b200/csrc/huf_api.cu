@@ -68,10 +68,47 @@ struct DevBuf {
   }
   template <typename T>
   T* as() { return reinterpret_cast<T*>(p); }
+  void release() {
+    if (p) cudaFree(p);  // (fails harmlessly once the runtime is shut down)
+    p = nullptr;
+    cap = 0;
+    dev = -1;
+  }
+  ~DevBuf() { release(); }
 };
 
+// Per-thread state of the single-buffer host calls: device buffers and one non-blocking stream
+// (never the legacy default stream, which would serialise against everything else the host
+// application runs on the device).
 struct Workspace {
   DevBuf in, out, sizes, offsets, misc, table;
+  cudaStream_t st = nullptr;
+  int dev = -1;
+  cudaError_t ready() {
+    int cur = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return e;
+    if (st && dev != cur) {
+      cudaStreamDestroy(st);
+      st = nullptr;
+    }
+    if (!st) {
+      e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      if (e != cudaSuccess) {
+        st = nullptr;
+        return e;
+      }
+      dev = cur;
+    }
+    return cudaSuccess;
+  }
+  void release() {
+    in.release(); out.release(); sizes.release(); offsets.release(); misc.release(); table.release();
+    if (st) cudaStreamDestroy(st);
+    st = nullptr;
+    dev = -1;
+  }
+  ~Workspace() { release(); }
 };
 thread_local Workspace g_ws;
 
@@ -107,9 +144,28 @@ struct Pipe {
     }
     return cudaSuccess;
   }
+  void release() {
+    in.release(); out.release(); sizes.release(); offsets.release(); packed.release(); misc.release();
+    if (st) cudaStreamDestroy(st);
+    st = nullptr;
+    if (meta) cudaFreeHost(meta);
+    meta = nullptr;
+    dev = -1;
+  }
+  ~Pipe() { release(); }
 };
 thread_local Pipe g_pipe[2];
 constexpr size_t kChunkBytes = (size_t)32 << 20;  // raw bytes per pipeline chunk
+
+// Every exit of a pipelined call -- the error returns included -- waits for both pipe streams:
+// copies queued against the caller's buffers must not outlive the call, and the next call must
+// find the pipes idle.
+struct PipeDrain {
+  ~PipeDrain() {
+    for (int i = 0; i < 2; ++i)
+      if (g_pipe[i].st) cudaStreamSynchronize(g_pipe[i].st);
+  }
+};
 
 struct DevInfo {
   int dev = -1;
@@ -183,21 +239,22 @@ int compress_host(int k, size_t block_size, const uint8_t* raw, size_t n, uint32
                   const void* d_table, int check_presence, std::vector<uint32_t>* sizes,
                   size_t* slot_stride_out) {
   Workspace& ws = g_ws;
+  CU(ws.ready());
   const size_t stride = hufb200_slot_stride(block_size, k);
   CU(ws.in.reserve(n + 16));
   CU(ws.out.reserve(stride * n_blocks));
   CU(ws.sizes.reserve(sizeof(uint32_t) * (n_blocks + 1)));
   CU(ws.misc.reserve(256));
-  if (n) CU(cudaMemcpyAsync(ws.in.p, raw, n, cudaMemcpyHostToDevice, 0));
-  CU(cudaMemsetAsync(ws.misc.p, 0, 4, 0));
+  if (n) CU(cudaMemcpyAsync(ws.in.p, raw, n, cudaMemcpyHostToDevice, ws.st));
+  CU(cudaMemsetAsync(ws.misc.p, 0, 4, ws.st));
   int rc = do_compress_dev(k, block_size, ws.in.as<uint8_t>(), n, n_blocks, ws.out.as<uint8_t>(), stride,
-                           ws.sizes.as<uint32_t>(), d_table, check_presence, ws.misc.as<uint32_t>(), 0);
+                           ws.sizes.as<uint32_t>(), d_table, check_presence, ws.misc.as<uint32_t>(), ws.st);
   if (rc) return rc;
   sizes->resize(n_blocks);
   uint32_t status = 0;
-  CU(cudaMemcpyAsync(sizes->data(), ws.sizes.p, sizeof(uint32_t) * n_blocks, cudaMemcpyDeviceToHost, 0));
-  CU(cudaMemcpyAsync(&status, ws.misc.p, 4, cudaMemcpyDeviceToHost, 0));
-  CU(cudaStreamSynchronize(0));
+  CU(cudaMemcpyAsync(sizes->data(), ws.sizes.p, sizeof(uint32_t) * n_blocks, cudaMemcpyDeviceToHost, ws.st));
+  CU(cudaMemcpyAsync(&status, ws.misc.p, 4, cudaMemcpyDeviceToHost, ws.st));
+  CU(cudaStreamSynchronize(ws.st));
   if (status) return fail(HUFB200_E_CORRUPT, "a symbol of the input has no code in the supplied table");
   *slot_stride_out = stride;
   return HUFB200_OK;
@@ -210,6 +267,15 @@ extern "C" {
 int hufb200_version(void) { return 100; }
 const char* hufb200_last_error(void) { return g_err; }
 uint64_t hufb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void hufb200_release_workspace(void) {
+  for (int i = 0; i < 2; ++i) {
+    if (g_pipe[i].st) cudaStreamSynchronize(g_pipe[i].st);
+    g_pipe[i].release();
+  }
+  if (g_ws.st) cudaStreamSynchronize(g_ws.st);
+  g_ws.release();
+}
 
 int hufb200_device_count(void) {
   int n = 0;
@@ -238,13 +304,14 @@ int hufb200_histogram_dev(const uint8_t* d_in, size_t n, uint64_t* d_out, void* 
 int hufb200_histogram64(const uint8_t* in, size_t n, uint64_t out[256]) {
   if (!out || (!in && n)) return fail(HUFB200_E_INVALID, "null pointer");
   Workspace& ws = g_ws;
+  CU(ws.ready());
   CU(ws.in.reserve(n + 16));
   CU(ws.misc.reserve(256 * sizeof(uint64_t)));
-  if (n) CU(cudaMemcpyAsync(ws.in.p, in, n, cudaMemcpyHostToDevice, 0));
-  int rc = hufb200_histogram_dev(ws.in.as<uint8_t>(), n, ws.misc.as<uint64_t>(), nullptr);
+  if (n) CU(cudaMemcpyAsync(ws.in.p, in, n, cudaMemcpyHostToDevice, ws.st));
+  int rc = hufb200_histogram_dev(ws.in.as<uint8_t>(), n, ws.misc.as<uint64_t>(), ws.st);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(out, ws.misc.p, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, 0));
-  CU(cudaStreamSynchronize(0));
+  CU(cudaMemcpyAsync(out, ws.misc.p, 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ws.st));
+  CU(cudaStreamSynchronize(ws.st));
   return HUFB200_OK;
 }
 
@@ -287,14 +354,15 @@ int hufb200_make_table(const uint32_t hist[256], uint16_t len_count[13], uint8_t
   if (!hist) return fail(HUFB200_E_INVALID, "null pointer");
   if (sizeof(HostTable) != table_bytes()) return fail(HUFB200_E_INVALID, "table layout mismatch");
   Workspace& ws = g_ws;
+  CU(ws.ready());
   CU(ws.misc.reserve(256 * sizeof(uint32_t)));
   CU(ws.table.reserve(table_bytes()));
-  CU(cudaMemcpyAsync(ws.misc.p, hist, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, 0));
-  CU(launch_make_table(ws.misc.as<uint32_t>(), nullptr, nullptr, 0, 0, ws.table.p, 0));
+  CU(cudaMemcpyAsync(ws.misc.p, hist, 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, ws.st));
+  CU(launch_make_table(ws.misc.as<uint32_t>(), nullptr, nullptr, 0, 0, ws.table.p, ws.st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   HostTable t;
-  CU(cudaMemcpyAsync(&t, ws.table.p, sizeof(t), cudaMemcpyDeviceToHost, 0));
-  CU(cudaStreamSynchronize(0));
+  CU(cudaMemcpyAsync(&t, ws.table.p, sizeof(t), cudaMemcpyDeviceToHost, ws.st));
+  CU(cudaStreamSynchronize(ws.st));
   if (len_count)
     for (int i = 0; i <= HUFB200_MAX_CODE_LEN; ++i) len_count[i] = t.len_count[i];
   if (sorted_syms) {
@@ -332,16 +400,17 @@ int decode_table_dump(const uint16_t len_count[13], const uint8_t* sorted_syms, 
   if (!len_count || !out || num_syms < 0 || num_syms > 256 || (!sorted_syms && num_syms))
     return fail(HUFB200_E_INVALID, "bad table arguments");
   Workspace& ws = g_ws;
+  CU(ws.ready());
   CU(ws.misc.reserve(1024));
   CU(ws.out.reserve(4096 * 4));
   uint8_t* d_lc = ws.misc.as<uint8_t>();
   uint8_t* d_sy = d_lc + 64;
-  CU(cudaMemcpyAsync(d_lc, len_count, 13 * sizeof(uint16_t), cudaMemcpyHostToDevice, 0));
-  if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, 0));
-  CU(launch_dump_dtable(reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, one_symbol, ws.out.as<uint8_t>(), 0));
+  CU(cudaMemcpyAsync(d_lc, len_count, 13 * sizeof(uint16_t), cudaMemcpyHostToDevice, ws.st));
+  if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, ws.st));
+  CU(launch_dump_dtable(reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, one_symbol, ws.out.as<uint8_t>(), ws.st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  CU(cudaMemcpyAsync(out, ws.out.p, one_symbol ? 4096 * 2 : 4096 * 4, cudaMemcpyDeviceToHost, 0));
-  CU(cudaStreamSynchronize(0));
+  CU(cudaMemcpyAsync(out, ws.out.p, one_symbol ? 4096 * 2 : 4096 * 4, cudaMemcpyDeviceToHost, ws.st));
+  CU(cudaStreamSynchronize(ws.st));
   return HUFB200_OK;
 }
 }  // namespace
@@ -367,7 +436,8 @@ int hufb200_compress(int k, const uint8_t* raw, size_t n, uint8_t* out, size_t c
   if (rc) return rc;
   *out_len = sizes[0];
   if (sizes[0] > cap) return fail(HUFB200_E_NOSPACE, "need %u bytes, have %zu", sizes[0], cap);
-  CU(cudaMemcpy(out, g_ws.out.p, sizes[0], cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(out, g_ws.out.p, sizes[0], cudaMemcpyDeviceToHost, g_ws.st));
+  CU(cudaStreamSynchronize(g_ws.st));
   return HUFB200_OK;
 }
 
@@ -379,13 +449,14 @@ int hufb200_compress_with_table(int k, const uint8_t* raw, size_t n, const uint1
   if (!out_len || (!raw && n) || !len_count || num_syms < 0 || num_syms > 256 || (!sorted_syms && num_syms))
     return fail(HUFB200_E_INVALID, "bad arguments");
   Workspace& ws = g_ws;
+  CU(ws.ready());
   CU(ws.misc.reserve(1024));
   CU(ws.table.reserve(table_bytes()));
   uint8_t* d_lc = ws.misc.as<uint8_t>() + 256;
   uint8_t* d_sy = d_lc + 64;
-  CU(cudaMemcpyAsync(d_lc, len_count, 13 * sizeof(uint16_t), cudaMemcpyHostToDevice, 0));
-  if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, 0));
-  CU(launch_make_table(nullptr, reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, 1, ws.table.p, 0));
+  CU(cudaMemcpyAsync(d_lc, len_count, 13 * sizeof(uint16_t), cudaMemcpyHostToDevice, ws.st));
+  if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, ws.st));
+  CU(launch_make_table(nullptr, reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, 1, ws.table.p, ws.st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   std::vector<uint32_t> sizes;
   size_t stride = 0;
@@ -393,7 +464,8 @@ int hufb200_compress_with_table(int k, const uint8_t* raw, size_t n, const uint1
   if (rc) return rc;
   *out_len = sizes[0];
   if (sizes[0] > cap) return fail(HUFB200_E_NOSPACE, "need %u bytes, have %zu", sizes[0], cap);
-  CU(cudaMemcpy(out, g_ws.out.p, sizes[0], cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(out, g_ws.out.p, sizes[0], cudaMemcpyDeviceToHost, g_ws.st));
+  CU(cudaStreamSynchronize(g_ws.st));
   return HUFB200_OK;
 }
 
@@ -416,25 +488,26 @@ int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_
   if (raw_size > cap) return fail(HUFB200_E_NOSPACE, "need %zu bytes, have %zu", raw_size, cap);
   if (raw_size > kMaxBlock) return fail(HUFB200_E_INVALID, "raw_size exceeds the 2^30 single-buffer limit");
   Workspace& ws = g_ws;
+  CU(ws.ready());
   CU(ws.in.reserve(n + 32));
   CU(ws.out.reserve(raw_size + 16));
   CU(ws.misc.reserve(256));
-  CU(cudaMemcpyAsync(ws.in.p, comp, n, cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(ws.in.p, comp, n, cudaMemcpyHostToDevice, ws.st));
   struct {
     unsigned long long off;
     uint32_t size;
     uint32_t status;
   } meta = {0ull, (uint32_t)n, 0u};
-  CU(cudaMemcpyAsync(ws.misc.p, &meta, sizeof(meta), cudaMemcpyHostToDevice, 0));
+  CU(cudaMemcpyAsync(ws.misc.p, &meta, sizeof(meta), cudaMemcpyHostToDevice, ws.st));
   uint8_t* m = ws.misc.as<uint8_t>();
   CU(launch_decompress(ws.in.as<uint8_t>(), reinterpret_cast<unsigned long long*>(m),
                        reinterpret_cast<uint32_t*>(m + 8), 1, k, 1, ws.out.as<uint8_t>(), raw_size,
-                       (uint32_t)(raw_size ? raw_size : 1), reinterpret_cast<uint32_t*>(m + 12), 0));
+                       (uint32_t)(raw_size ? raw_size : 1), reinterpret_cast<uint32_t*>(m + 12), ws.st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   uint32_t status = 0;
-  CU(cudaMemcpyAsync(&status, m + 12, 4, cudaMemcpyDeviceToHost, 0));
-  if (raw_size) CU(cudaMemcpyAsync(out, ws.out.p, raw_size, cudaMemcpyDeviceToHost, 0));
-  CU(cudaStreamSynchronize(0));
+  CU(cudaMemcpyAsync(&status, m + 12, 4, cudaMemcpyDeviceToHost, ws.st));
+  if (raw_size) CU(cudaMemcpyAsync(out, ws.out.p, raw_size, cudaMemcpyDeviceToHost, ws.st));
+  CU(cudaStreamSynchronize(ws.st));
   if (status) return fail(HUFB200_E_CORRUPT, "malformed compressed buffer");
   return HUFB200_OK;
 }
@@ -474,6 +547,7 @@ int hufb200_compress_blocks(int k, size_t block_size, const uint8_t* raw, size_t
   size_t per = kChunkBytes / block_size;  // blocks per chunk
   if (per < 1) per = 1;
   const size_t n_chunks = (nb + per - 1) / per;
+  PipeDrain drain;
   size_t total = index_end;  // running container size
   bool fits = index_end <= cap;
   struct Pending {
@@ -585,6 +659,7 @@ int hufb200_decompress_blocks(const uint8_t* c, size_t n, uint8_t* out, size_t c
   }
   if (sum != payload_n) return fail(HUFB200_E_CORRUPT, "block sizes do not add up to the payload size");
   // chunked two-stream pipeline: payload host->device, decode, raw device->host
+  PipeDrain drain;
   size_t per = kChunkBytes / bs;
   if (per < 1) per = 1;
   const size_t n_chunks = (nb + per - 1) / per;

@@ -149,7 +149,7 @@ k_histogram(const uint8_t* __restrict__ in, uint64_t n, unsigned long long* __re
   if (beg < n) {
     uint64_t len = per * 16;
     if (beg + len > n) len = n - beg;
-    // 32-bit lane counters: a CTA's share is processed in pieces of < 2^32 bytes
+    // 32-bit lane counters: the launcher sizes the grid so that a CTA's share stays below 2^32 bytes
     bins_accumulate(bins, in + beg, len, threadIdx.x, blockDim.x);
   }
   __syncthreads();
@@ -1668,14 +1668,14 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
   const bool long_slices = (block_size + (uint32_t)K - 1) / (uint32_t)K > (uint32_t)kStageSlice;
   auto kernel = long_slices ? k_compress_blocks<true> : k_compress_blocks<false>;
   // the attribute is per device and per kernel: remember where it has been set (bit per ordinal)
-  static thread_local unsigned long long configured[2] = {0, 0};
+  static std::atomic<unsigned long long> configured[2];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  if (dev >= 64 || !((configured[long_slices] >> dev) & 1ull)) {
+  if (dev >= 64 || !((configured[long_slices].load(std::memory_order_acquire) >> dev) & 1ull)) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompSmem));
     if (e != cudaSuccess) return e;
-    if (dev < 64) configured[long_slices] |= 1ull << dev;
+    if (dev < 64) configured[long_slices].fetch_or(1ull << dev, std::memory_order_release);
   }
   kernel<<<grid, kCompThreads, sizeof(CompSmem), st>>>(d_raw, n, block_size, K, n_blocks, d_out, slot_stride, d_sizes,
                                                        reinterpret_cast<const HufTable*>(d_table), check_presence, d_status,
@@ -1694,9 +1694,21 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
   if (n_blocks == 0) return cudaSuccess;
   const int nthreads = ((K * bpc + 31) / 32) * 32;
   const size_t smem = decompress_smem_bytes(K, bpc);
-  if (smem > 48 * 1024) {  // opt-in beyond the default limit (per device, so set whenever it is needed)
-    cudaError_t e = cudaFuncSetAttribute(k_decompress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {  // opt-in beyond the 48 KiB default: the attribute is per device and per kernel and shared by
+     // all host threads, so it is set once per device, to the device's limit -- never per launch
+     // (two threads decoding with different K would otherwise lower it under each other)
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull)) {
+      int optin = 0;
+      e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(k_decompress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+      if (e != cudaSuccess) return e;
+      if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
+    }
   }
   const uint32_t grid = (n_blocks + bpc - 1) / bpc;
   k_decompress_blocks<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n,

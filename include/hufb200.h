@@ -48,6 +48,11 @@ HUFB200_API const char* hufb200_last_error(void); /* thread-local message of the
 HUFB200_API int hufb200_device_count(void);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 HUFB200_API uint64_t hufb200_launch_count(void);
+/* The host-pointer entry points keep per-thread device buffers, pinned words and streams between
+ * calls (grow-only, sized by the largest call so far).  This frees the calling thread's; they are
+ * also freed when the thread exits.  The reference keeps no state: call this
+ * where that matters. */
+HUFB200_API void hufb200_release_workspace(void);
 
 /* ---- histogram: huffman::MakeHistogram, codec/histogram.h:12, codec/histogram.cpp:193-201 ---- */
 /* n < 2^32 (ByteHistogram is u32, codec/histogram.h:10). */
@@ -75,10 +80,13 @@ HUFB200_API int hufb200_decode_table1x(const uint16_t len_count[13], const uint8
  * codec/huffman.h:9-12, codec/huffman.cpp:738-846 / :892-960 ---- */
 /* Upper bound of the compressed size of n raw bytes with k streams. */
 HUFB200_API size_t hufb200_compress_bound(size_t n, int k);
-/* out receives exactly the bytes CompressMulti<k>(raw) returns.  n < 2^32. */
+/* out receives exactly the bytes CompressMulti<k>(raw) returns.  n <= 2^30: the format's offsets
+ * are 32-bit and the reference computes them as int (codec/huffman.cpp:772); larger inputs get
+ * HUFB200_E_INVALID -- cut them into blocks (hufb200_compress_blocks). */
 HUFB200_API int hufb200_compress(int k, const uint8_t* raw, size_t n, uint8_t* out, size_t cap,
                      size_t* out_len);
-/* out receives exactly the bytes DecompressMulti<k>(comp) returns. */
+/* out receives exactly the bytes DecompressMulti<k>(comp) returns.  The size comes from the
+ * buffer's untrusted raw_size field: it is checked against cap before anything is allocated. */
 HUFB200_API int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_t cap,
                        size_t* out_len);
 /* raw_size field of a compressed buffer (ParseCompressedHeader, codec/huffman.cpp:714-718). */

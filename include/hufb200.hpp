@@ -50,6 +50,8 @@ std::string DecompressMulti(std::string_view compressed) {
   size_t raw_size = 0;
   check(hufb200_raw_size(reinterpret_cast<const uint8_t*>(compressed.data()), compressed.size(), &raw_size),
         "hufb200_raw_size");
+  // raw_size is untrusted; the library's single-buffer limit (2^30, codec/huffman.cpp:772) bounds the allocation
+  if (raw_size > (size_t(1) << 30)) throw std::runtime_error("hufb200: header claims more than 2^30 raw bytes");
   std::string out(raw_size, '\0');
   size_t n = 0;
   check(hufb200_decompress(K, reinterpret_cast<const uint8_t*>(compressed.data()), compressed.size(),

@@ -324,3 +324,153 @@ def test_staged_mode_for_long_slices_and_its_fallback(huf, oracle):
     cd = oracle.make_coding(oracle.histogram(one_hot.tobytes()))
     assert int(cd["code_len"][one_hot[5 * sl:6 * sl]].sum()) > 1276 * 32
     assert int(cd["code_len"][one_hot].sum()) / bs * sl < 1276 * 28
+
+
+def test_corruption_is_reported_not_decoded(huf):
+    """Detectable corruption must come back as HUFB200_E_CORRUPT, not as garbage with status OK:
+    an over- or under-subscribed length table (Kraft sum != 1), a payload whose codes do not end
+    where the stream ends, end offsets that are not cumulative."""
+    data = biased(300_000, seed=9)
+    for k in (4, 32):
+        good = bytearray(huf.compress(k, data))
+        mask = int.from_bytes(good[4:8], "little")
+        npop = bin(mask).count("1")
+        # (a) length table: one code more / one code less of some length
+        for delta in (+1, -1):
+            bad = bytearray(good)
+            bad[8 + npop - 1] = (bad[8 + npop - 1] + delta) & 0xff
+            with pytest.raises(huf.HufError) as ei:
+                huf.decompress(k, bytes(bad))
+            assert ei.value.code == -4
+        # (b) payload: a flipped byte garbles a few symbols, then a Huffman decoder falls back into
+        #     step; it is caught whenever the garbled part decodes to a different NUMBER of symbols
+        #     (the stream then does not end on its last byte).  The format has no checksum, so
+        #     flips that keep the count are undetectable -- here, by the reference, by anyone.
+        hits = 0
+        rng = np.random.default_rng(k)
+        for trial in range(30):
+            bad = bytearray(good)
+            pos = int(rng.integers(len(good) // 2, len(good) - 64))
+            bad[pos] ^= 0x55
+            try:
+                huf.decompress(k, bytes(bad))  # (a flip in slop or padding bits changes nothing)
+            except huf.HufError as e:
+                assert e.code == -4
+                hits += 1
+        assert hits >= 1, hits
+        # (c) end offsets: swap two neighbours (no longer cumulative)
+        if k > 2:
+            nsyms = sum(good[8: 8 + npop]) or 256
+            ends = 8 + npop + nsyms
+            bad = bytearray(good)
+            bad[ends: ends + 4], bad[ends + 4: ends + 8] = good[ends + 4: ends + 8], good[ends: ends + 4]
+            with pytest.raises(huf.HufError) as ei:
+                huf.decompress(k, bytes(bad))
+            assert ei.value.code == -4
+        assert huf.decompress(k, bytes(good)) == data
+
+
+def test_corrupt_chunk_with_pinned_buffers_leaves_nothing_in_flight(huf):
+    """A container of several pipeline chunks whose FIRST chunk is corrupt, decoded into pinned
+    memory: the call must return E_CORRUPT only after every copy it queued against the caller's
+    buffers has finished (the output buffer is overwritten right after the call; a later decode
+    must be unaffected)."""
+    import ctypes as C
+    import torch
+    data = biased(100 << 20, seed=21)  # 100 MiB -> four 32 MiB chunks
+    k, bs = 32, 131072
+    cont = huf.compress_blocks(k, bs, data)
+    L = huf.load()
+    host_c = torch.frombuffer(bytearray(cont), dtype=torch.uint8).pin_memory()
+    host_o = torch.empty(len(data), dtype=torch.uint8).pin_memory()
+    olen = C.c_size_t(0)
+    info = huf.binding.container_info(np.frombuffer(cont, dtype=np.uint8))
+    first_payload = 32 + 4 * info["n_blocks"]
+    saved = host_c[first_payload + 4: first_payload + 8].clone()
+    host_c[first_payload + 4: first_payload + 8] = torch.tensor([0xff, 0xff, 0x00, 0x00], dtype=torch.uint8)  # len_mask
+    rc = L.hufb200_decompress_blocks(C.c_void_p(host_c.data_ptr()), len(cont), C.c_void_p(host_o.data_ptr()),
+                                     len(data), C.byref(olen))
+    assert rc == -4
+    host_o.fill_(0xAB)  # would race with a copy still in flight
+    torch.cuda.synchronize()
+    assert bool((host_o == 0xAB).all())
+    host_c[first_payload + 4: first_payload + 8] = saved
+    rc = L.hufb200_decompress_blocks(C.c_void_p(host_c.data_ptr()), len(cont), C.c_void_p(host_o.data_ptr()),
+                                     len(data), C.byref(olen))
+    assert rc == 0 and olen.value == len(data)
+    assert host_o.numpy().tobytes() == data
+
+
+def test_cpp_policy_class_runs_on_the_device(huf, oracle):
+    """include/hufb200.hpp's HuffmanCompressorB200<K> -- the template argument the reference's
+    TYPED_TEST_SUITE / DEFINE_BENCHMARKS take (codec/huffman_test.cpp:47-54,
+    codec/huffman_benchmark.cpp:252-281) -- built with g++ and RUN on the device over the
+    reference's CompressorTest inputs: Decompress(Compress(x)) == x inside the program, and the
+    bytes it returns equal the oracle's."""
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = r"""
+#include "hufb200.hpp"
+#include <cstdio>
+#include <fstream>
+#include <iterator>
+#include <vector>
+template <int K> int run(const std::vector<std::string>& in, std::vector<std::string>* out) {
+  using T = hufb200::HuffmanCompressorB200<K>;
+  for (const std::string& raw : in) {
+    std::string c = T::Compress(raw);
+    if (T::Decompress(c) != raw) { std::printf("%s: round trip differs\n", T::name().c_str()); return 1; }
+    out->push_back(c);
+  }
+  return 0;
+}
+int main(int argc, char** argv) {
+  const int k = std::atoi(argv[1]);
+  std::ifstream f(argv[2], std::ios::binary);
+  std::string all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  std::vector<std::string> in, out;
+  for (size_t p = 0; p + 4 <= all.size();) {
+    uint32_t n; std::memcpy(&n, all.data() + p, 4); p += 4;
+    in.emplace_back(all.substr(p, n)); p += n;
+  }
+  int rc = 3;
+  try {
+    switch (k) {
+      case 1: rc = run<1>(in, &out); break;
+      case 4: rc = run<4>(in, &out); break;
+      case 8: rc = run<8>(in, &out); break;
+      case 16: rc = run<16>(in, &out); break;
+      case 32: rc = run<32>(in, &out); break;
+      case 48: rc = run<48>(in, &out); break;
+    }
+    hufb200::ByteHistogram h = hufb200::MakeHistogram(in.empty() ? std::string() : in[1]);
+    unsigned long long tot = 0; for (uint32_t c : h) tot += c;
+    if (!in.empty() && tot != in[1].size()) rc |= 4;
+  } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
+  std::ofstream o(argv[3], std::ios::binary);
+  for (const std::string& c : out) { uint32_t n = (uint32_t)c.size(); o.write((const char*)&n, 4); o.write(c.data(), n); }
+  return rc;
+}
+"""
+    libdir = os.path.dirname(huf.lib_path())
+    exe = "/tmp/hufb200_policy_gpu"
+    with open(exe + ".cpp", "w") as f:
+        f.write("#include <cstring>\n#include <cstdlib>\n" + src)
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"), exe + ".cpp", "-o", exe,
+                        "-L", libdir, "-lhufb200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cases = [d for _, d in reference_test_cases()[:12] + extra_cases()]
+    with open(exe + ".in", "wb") as f:
+        for d in cases:
+            f.write(struct.pack("<I", len(d)) + d)
+    for k in (1, 4, 8, 16, 32, 48):
+        rc = subprocess.run([exe, str(k), exe + ".in", exe + ".out"], capture_output=True, text=True)
+        assert rc.returncode == 0, (k, rc.stdout, rc.stderr)
+        blob = open(exe + ".out", "rb").read()
+        p = 0
+        for d in cases:
+            (n,) = struct.unpack_from("<I", blob, p)
+            assert blob[p + 4: p + 4 + n] == oracle.compress(k, d), (k, len(d))
+            p += 4 + n
+        assert p == len(blob)
