@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--shared-table", action="store_true", help="one table for all blocks (histogram all-reduce)")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0, help="length of the sustained loop (0 = skip)")
+    ap.add_argument("--no-shared-leg", action="store_true", help="skip the shared-table sub-record")
+    ap.add_argument("--parity-blocks", type=int, default=256, help="blocks compared with the CPU checker in the cpu_baseline leg")
     return ap.parse_args()
 
 
@@ -69,8 +72,10 @@ def cpu_sample(args, n_blocks=64):
     return data, n_blocks
 
 
-def cpu_reference_run(args, seconds, threads):
-    """Times the reference's CPU codec on a bounded sample; returns (dict, kind)."""
+def cpu_reference_run(args, seconds, threads, breadth=False):
+    """Times the reference's CPU codec on a bounded sample; returns the cpu_baseline record.
+    breadth: additionally the reference's published method (one thread, README.md:38) for
+    K in {4,8,16,32,48} and its histogram functions."""
     import numpy as np
     from _libs import Oracle, Ref, have_ref
     data, nb = cpu_sample(args)
@@ -79,20 +84,47 @@ def cpu_reference_run(args, seconds, threads):
         r = Ref()
         res = {}
         # scalar is what the GPU output is compared with; the AVX-512 paths are the reference's fastest
-        variants = [("scalar", r.SCALAR)]
         flags = open("/proc/cpuinfo").read()
         avx = all(f in flags for f in ("avx512f", "avx512bw", "avx512vbmi"))
-        if avx and args.k % 8 == 0:
-            variants += [("avx512_gather", r.GATHER), ("avx512_permute", r.PERMUTE)]
-        for name, v in variants:
-            c, ratio = r.bench(args.k, v, 0, data, args.block, args.block, nb, threads, seconds)
-            d, _ = r.bench(args.k, v, 1, data, args.block, args.block, nb, threads, seconds)
-            res[name] = {"compress_GBps": c / GB, "decompress_GBps": d / GB,
-                         "roundtrip_GBps": 1.0 / (GB / c + GB / d), "ratio": ratio}
+
+        def variants(k):
+            v = [("scalar", r.SCALAR)] if k in (1, 2, 4, 8, 16, 32, 48) else []
+            if avx and k % 8 == 0:
+                v += [("avx512_gather", r.GATHER), ("avx512_permute", r.PERMUTE)]
+            return v
+
+        def run(k, v, thr, secs):
+            c, ratio = r.bench(k, v, 0, data, args.block, args.block, nb, thr, secs)
+            d, _ = r.bench(k, v, 1, data, args.block, args.block, nb, thr, secs)
+            return {"compress_GBps": c / GB, "decompress_GBps": d / GB, "roundtrip_GBps": 1.0 / (GB / c + GB / d),
+                    "ratio": ratio}
+
+        for name, v in variants(args.k):
+            res[name] = run(args.k, v, threads, seconds)
         best = max(res.values(), key=lambda x: x["roundtrip_GBps"])
-        return {"value": best["roundtrip_GBps"], "unit": UNIT, "cores": threads, "kind": "reference",
-                "sample": sample, "avx512": avx, "paths": res,
-                "huff0": "unavailable (FiniteStateEntropy source not vendored; README: 1946/3636 MiB/s on a 9950X)"}
+        out = {"value": best["roundtrip_GBps"], "unit": UNIT, "cores": threads, "kind": "reference",
+               "sample": sample, "avx512": avx, "paths": res,
+               "huff0": "unavailable (FiniteStateEntropy source not vendored; README: 1946/3636 MiB/s on a 9950X)"}
+        if breadth:
+            short = min(0.25, seconds)
+            one = {}
+            for k in (4, 8, 16, 32, 48):
+                for name, v in variants(k):
+                    one[f"{name}/K{k}"] = run(k, v, 1, short)
+            out["single_thread"] = {"method": "one thread, the reference's published method (README.md:38)",
+                                    "seconds_per_case": short, "paths": one}
+            hsample = data[: min(data.size, 8 << 20)]
+            hist = {}
+            for which, name in ((0, "MakeHistogram"), (1, "Simple"), (2, "Multi"), (3, "Vectorized"), (4, "GatherScatter")):
+                try:
+                    hist[name] = {"one_thread_GBps": r.lib.ref_bench_histogram(which, hsample.ctypes.data_as(
+                        C.POINTER(C.c_uint8)), hsample.size, 1, short) / GB,
+                        "all_cores_GBps": r.lib.ref_bench_histogram(which, hsample.ctypes.data_as(
+                            C.POINTER(C.c_uint8)), hsample.size, threads, short) / GB}
+                except Exception as e:  # the shim knows fewer variants
+                    hist[name] = str(e)
+            out["histogram"] = hist
+        return out
     # oracle port, single thread
     o = Oracle()
     blk = data[: args.block].tobytes()
@@ -195,6 +227,60 @@ class ClockSampler(threading.Thread):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- parity sample
+
+def parity_sample(args, huf, codec, raw, slots, sizes, status, sh_table):
+    """Compares `--parity-blocks` seeded blocks of the GPU output with the CPU checker."""
+    import numpy as np
+    import torch
+    from _parity import compare_blocks
+    n = raw.numel()
+    nb = codec.n_blocks(n)
+    rng = np.random.default_rng(20261018)
+    pick = sorted(set([0, nb - 1] + [int(b) for b in rng.integers(0, nb, max(0, args.parity_blocks - 2))]))
+    raw_h = raw.cpu().numpy()
+    codec.compress(raw, slots=slots, sizes=sizes, status=status)
+    torch.cuda.synchronize()
+    sz = sizes[:nb].cpu().numpy().astype(np.int64)
+    offs = np.arange(nb, dtype=np.int64) * codec.slot_stride
+    sl = slots.cpu().numpy()
+    name, checked, bad = compare_blocks(raw_h, sl, offs, sz, args.k, args.block, blocks=pick)
+    out = {"checker": name, "per_block_tables": {"blocks": checked, "mismatches": len(bad)}}
+    assert not bad, f"parity: {len(bad)} of {checked} blocks differ from {name}: {bad[:8]}"
+    if sh_table is not None:
+        from _libs import Oracle
+        o = Oracle()
+        codec.compress(raw, slots=slots, sizes=sizes, table=sh_table, status=status)
+        torch.cuda.synchronize()
+        sz = sizes[:nb].cpu().numpy().astype(np.int64)
+        sl = slots.cpu().numpy()
+        # the table the device built from the (all-reduced) histogram, as the header of block 0 carries it
+        b0 = sl[: int(sz[0])].tobytes()
+        mask = int.from_bytes(b0[4:8], "little")
+        lens = [l for l in range(13) if (mask >> l) & 1]
+        counts = list(b0[8: 8 + len(lens)])
+        if len(lens) == 1 and counts[0] == 0:
+            counts[0] = 256
+        lc = np.zeros(13, dtype=np.uint16)
+        for l, c in zip(lens, counts):
+            lc[l] = c
+        nsyms = int(lc.sum())
+        syms = b0[8 + len(lens): 8 + len(lens) + nsyms]
+        # ... which must be the table of the global histogram
+        want = o.make_coding(np.bincount(raw_h, minlength=256).astype(np.uint32))
+        ok_table = bool(np.array_equal(want["len_count"], lc)) and want["sorted_syms"] == syms
+        bad_s = 0
+        sub = pick[: max(8, len(pick) // 8)]
+        for b in sub:
+            lo = b * args.block
+            w = o.compress_with_table(args.k, raw_h[lo: lo + args.block].tobytes(), lc, syms)
+            if w != sl[offs[b]: offs[b] + int(sz[b])].tobytes():
+                bad_s += 1
+        out["shared_table"] = {"blocks": len(sub), "mismatches": bad_s, "table_equals_global_histogram_table": ok_table}
+        assert bad_s == 0 and ok_table, "parity: shared-table blocks differ from the oracle"
+    return out
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -309,6 +395,82 @@ def run_ours(args):
     torch.cuda.synchronize()
     hist_ms = h0.elapsed_time(h1) / 10
 
+    # ---- sustained: the same step in a seconds-long loop (the timed region above is a burst of
+    # args.steps steps), clocks sampled throughout
+    sustained = None
+    if args.sustained_seconds > 0:
+        s_sampler = ClockSampler(local)
+        per = max(1e-3, elapsed_ms / args.steps * 1e-3)
+        n_sus = max(args.steps, int(args.sustained_seconds / per) + 1)
+        barrier()
+        s_sampler.start()
+        s0, s1 = ev(), ev()
+        s0.record()
+        for _ in range(n_sus):
+            step()
+        s1.record()
+        barrier()
+        s_clocks = s_sampler.result()
+        sus_ms = s0.elapsed_time(s1)
+        if world > 1:
+            t = torch.tensor([sus_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sus_ms = float(t.item())
+        sustained = {"value": world * n * n_sus / (sus_ms * 1e-3) / GB, "unit": UNIT, "steps": n_sus,
+                     "seconds": sus_ms * 1e-3, "clocks": s_clocks}
+
+    # ---- shared-table mode (the one collective of the path): histogram kernel -> all-reduce of
+    # 256 x i64 over NCCL -> table build -> compress with that table, every rank on its shard
+    shared = None
+    if not args.no_shared_leg:
+        sh_hist = torch.empty(256, dtype=torch.int64, device=dev)
+        sh_table = torch.empty(codec.table_bytes, dtype=torch.uint8, device=dev)
+        sh_steps = max(3, min(args.steps, 10))
+
+        def shared_step(evs=None):
+            if evs:
+                evs[0].record()
+            codec.histogram(raw, out=sh_hist)
+            if evs:
+                evs[1].record()
+            huf.sharded.allreduce_histogram(sh_hist)
+            if evs:
+                evs[2].record()
+            codec.build_table(sh_hist, out=sh_table)
+            if evs:
+                evs[3].record()
+            codec.compress(raw, slots=slots, sizes=sizes, table=sh_table, status=status)
+            if evs:
+                evs[4].record()
+
+        for _ in range(3):
+            shared_step()
+        sh_events = [[ev() for _ in range(5)] for _ in range(sh_steps)]
+        barrier()
+        for i in range(sh_steps):
+            shared_step(sh_events[i])
+        barrier()
+        avg = lambda a, b: sum(e[a].elapsed_time(e[b]) for e in sh_events) / sh_steps
+        sh_total_ms = avg(0, 4)
+        if world > 1:
+            t = torch.tensor([sh_total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sh_total_ms = float(t.item())
+        # the shared table must decode: round trip on the device
+        codec.decompress(slots, offsets, sizes, n, out=out, status=status)
+        torch.cuda.synchronize()
+        sh_ok = int(status.item()) == 0 and bool(torch.equal(out, raw))
+        sh_rho = int(sizes[:nb].to(torch.int64).sum().item()) / n
+        shared = {"GBps": world * n / (sh_total_ms * 1e-3) / GB, "ms_per_step": sh_total_ms,
+                  "histogram_ms": avg(0, 1), "allreduce_us": 1e3 * avg(1, 2), "table_build_us": 1e3 * avg(2, 3),
+                  "compress_ms": avg(3, 4), "compression_ratio": sh_rho, "roundtrip_ok": sh_ok,
+                  "collective": f"all_reduce(SUM) of 256 x int64 over {'NCCL, ' + str(world) + ' ranks' if world > 1 else 'no process group (1 rank: no-op)'}"}
+        assert sh_ok, "shared-table round trip mismatch"
+        shared["_table"] = sh_table  # kept for the parity sample of the cpu_baseline leg
+        # back to per-block tables for what follows
+        codec.compress(raw, slots=slots, sizes=sizes, status=status)
+        torch.cuda.synchronize()
+
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -342,7 +504,69 @@ def run_ours(args):
         e2e = {"value": world * n / dt / GB, "unit": UNIT, "h2d_bytes_per_step": n + clen.value,
                "d2h_bytes_per_step": clen.value + n, "ms_per_step": 1e3 * dt,
                "api": "hufb200_compress_blocks + hufb200_decompress_blocks (host pointers, pinned)"}
-        del host_raw, host_comp, host_out
+
+        # pure-copy ceiling of the same step: the same byte counts over PCIe with nothing else --
+        # first n bytes up while clen bytes come down (the compress call), then clen up while n
+        # come down (the decompress call); pinned memory, two streams, full duplex
+        csz = clen.value
+        dev_a = torch.empty(n, dtype=torch.uint8, device=dev)
+        dev_b = torch.empty(n, dtype=torch.uint8, device=dev)
+        st_up, st_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def copy_step():
+            for up, dn in ((n, csz), (csz, n)):
+                with torch.cuda.stream(st_up):
+                    dev_a[:up].copy_(host_raw[:up], non_blocking=True)
+                with torch.cuda.stream(st_dn):
+                    host_out[:dn].copy_(dev_b[:dn], non_blocking=True)
+                st_up.synchronize()
+                st_dn.synchronize()
+
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            copy_step()
+        torch.cuda.synchronize()
+        dtc = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dtc], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtc = float(t.item())
+        e2e["pcie_ceiling_GBps"] = world * n / dtc / GB
+        e2e["pcie_ceiling_ms_per_step"] = 1e3 * dtc
+        e2e["fraction_of_pcie_ceiling"] = dtc / dt
+        del dev_a, dev_b
+
+        # the same calls with PAGEABLE host memory (what a std::string caller of the policy class
+        # has): the driver stages such copies through its own pinned buffers
+        import numpy as np_
+        pg_raw = np_.empty(n, dtype=np_.uint8)
+        pg_raw[:] = host_raw.numpy()
+        pg_comp = np_.empty(bound, dtype=np_.uint8)
+        pg_out = np_.empty(n, dtype=np_.uint8)
+
+        def pageable_step():
+            huf.binding.check(L.hufb200_compress_blocks(args.k, args.block, C.c_void_p(pg_raw.ctypes.data), n,
+                                                        C.c_void_p(pg_comp.ctypes.data), bound, C.byref(clen)))
+            huf.binding.check(L.hufb200_decompress_blocks(C.c_void_p(pg_comp.ctypes.data), clen.value,
+                                                          C.c_void_p(pg_out.ctypes.data), n, C.byref(olen)))
+
+        pageable_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.e2e_steps - 1)):
+            pageable_step()
+        torch.cuda.synchronize()
+        dtp = (time.perf_counter() - t0) / max(1, args.e2e_steps - 1)
+        assert olen.value == n and np_.array_equal(pg_out, pg_raw), "pageable e2e round trip mismatch"
+        if world > 1:
+            t = torch.tensor([dtp], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtp = float(t.item())
+        e2e["pageable"] = {"value": world * n / dtp / GB, "unit": UNIT, "ms_per_step": 1e3 * dtp,
+                           "note": "same calls, pageable host buffers (driver-staged copies)"}
+        del host_raw, host_comp, host_out, pg_raw, pg_comp, pg_out
 
     if rank == 0:
         peaks = {}
@@ -381,8 +605,17 @@ def run_ours(args):
         }
         if e2e:
             res["e2e"] = e2e
+        if sustained:
+            res["sustained"] = sustained
+        sh_table = shared.pop("_table") if shared else None
+        if shared:
+            res["shared_table"] = shared
         if not args.no_cpu_baseline and world == 1:
-            res["cpu_baseline"] = cpu_reference_run(args, args.cpu_seconds, os.cpu_count() or 1)
+            res["cpu_baseline"] = cpu_reference_run(args, args.cpu_seconds, os.cpu_count() or 1, breadth=True)
+            # the checker's other job in this leg: a seeded sample of the blocks the timed steps
+            # produced, byte for byte against the CPU implementation (per-block tables), and the
+            # same for shared-table mode against compress-with-that-table
+            res["cpu_baseline"]["parity"] = parity_sample(args, huf, codec, raw, slots, sizes, status, sh_table)
         print(json.dumps(res))
     if world > 1:
         dist.barrier()
