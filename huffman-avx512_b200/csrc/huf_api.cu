@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -200,15 +201,22 @@ constexpr size_t kContainerHeader = 32;
 #define HUF_DEC_LANES 64
 #endif
 int decode_bpc(int k) {
+  static const int forced = [] {  // tuning aid: HUFB200_DEC_LANES overrides the lanes per decode CTA
+    const char* e = getenv("HUFB200_DEC_LANES");
+    const int v = e ? atoi(e) : 0;
+    return v >= 32 && v <= 256 ? v : 0;
+  }();
+  // with 32 or more streams per table, four-warp CTAs measured best (profiles/r2_decode_table_bits.md)
+  const int lanes_target = forced ? forced : (k >= 32 ? 2 * HUF_DEC_LANES : HUF_DEC_LANES);
   int best = 1;
   double best_util = 0.0;
   for (int b = 1; b <= 16; ++b) {
     const int lanes = b * k;
-    if (b > 1 && lanes > 2 * HUF_DEC_LANES) break;
+    if (b > 1 && (lanes > 2 * lanes_target || lanes > 256)) break;
     const double util = (double)lanes / (double)((lanes + 31) / 32 * 32);
-    const bool big_enough = lanes >= HUF_DEC_LANES;
+    const bool big_enough = lanes >= lanes_target;
     // until the target size is reached more lanes are always better; beyond it only a better fill counts
-    if (b == 1 || util > best_util + 1e-9 || (best * k < HUF_DEC_LANES && util >= best_util - 0.02)) {
+    if (b == 1 || util > best_util + 1e-9 || (best * k < lanes_target && util >= best_util - 0.02)) {
       best = b;
       best_util = util;
     }

@@ -12,6 +12,7 @@
 //
 // Reference behaviour: ahartik/huffman-avx512 codec/huffman.cpp, codec/histogram.cpp.
 #include <atomic>
+#include <cstdlib>
 #include <type_traits>
 
 #include "huf_device.cuh"
@@ -1107,15 +1108,19 @@ struct DecBlockInfo {
 //   entry: byte0..2 = symbols, bits 24..27 = stream bits consumed, bits 30..31 = symbol count.
 //   BITS = 12, MAXSYM = 2: exactly the reference's two-symbol table (pair iff l1+l2 <= 12, :653);
 //   BITS = 12, MAXSYM = 1: the reference's Decoder1x.  Both are only dumped for parity tests.
-//   BITS = 11, MAXSYM = 3, EXT: what the decode kernel uses: three symbols per lookup cut the
-//     lookups, ~8.5 KiB instead of 16 KiB per block keeps more stream groups resident.  11 bits
-//     cannot resolve a 12-bit code; the canonical code puts the 12-bit codes last, i.e. they own
-//     the prefixes p11 >= P (P = first 12-bit code >> 1), and behind the 11-bit part the table
-//     continues 12-bit-granular: entry P + j holds the j-th 12-bit code.  With p11 / p12 = the
-//     window's first 11 / 12 bits the lookup index is max(p11, p12 - P): for p11 < P the first
-//     wins (p12 - P = p11 + (p11 - P) + bit <= p11), for p11 >= P the second (>= p11), and
-//     p12 - P = P + (p12 - 2P) -- no branch, no fix-up after the load.  A complete code with
-//     n12 12-bit codes has P = 2048 - n12/2, so the table has 2048 + n12/2 <= 2176 entries.
+//   BITS = 9..11, MAXSYM = 3, EXT: what the decode kernel uses (BITS chosen from the stream count:
+//     few streams per block mean few lanes per table, so the table must be small to keep lanes
+//     resident).  Up to three symbols per lookup.  BITS bits cannot resolve a longer code; the
+//     canonical code orders codes by length, so the codes of each length l > BITS own one
+//     contiguous range of the code space, and behind the BITS-bit part (prefixes below P = first
+//     longer code >> (12 - BITS)) the table continues with one entry per longer code, length by
+//     length.  With p_l = the window's first l bits, level l addresses entry
+//     base_l + p_l - (first l-bit code >> (12 - l)), and the right level is the one with the
+//     LARGEST index: a coarser level counts the longer codes in fractions of its unit (never more
+//     than their number), a finer one is negative below its range.  So the lookup index is
+//     max over l = BITS..12 of (p_l + c_l), c_l per block -- no branch, nothing after the load.
+//     At most 256 codes in all, so the table has fewer than 2^BITS + 256 entries (2^11 + 128 for
+//     BITS = 11, where every dead prefix holds exactly two codes).
 // L1 (u8 per entry: the first code's own length, 15 = none) is scratch that may be reused
 // afterwards; the first symbol sits in byte 0 of T from the first pass on and never changes.
 template <int BITS, int MAXSYM, bool EXT = false>
@@ -1157,20 +1162,41 @@ __device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms,
     T[e] = out | (nb << 24) | (n << 30);
   }
   __syncthreads();
-  if (EXT) {  // the 12-bit codes, one entry each, from index P on (over the dead 11-bit entries)
-    const uint32_t v12 = bi->code_end[kMaxCodeLen - 1];  // first 12-bit code, left-aligned
-    const uint32_t P = v12 >> 1;
-    const uint32_t n12 = bi->code_end[kMaxCodeLen] - v12;
-    for (uint32_t j = tid; j < n12; j += nthreads) {
-      const uint32_t idx = bi->first_idx[kMaxCodeLen] + j;
-      T[P + j] = (idx < bi->num_syms ? syms[idx] : 0u) | (12u << 24) | (1u << 30);
+  if (EXT) {  // the codes longer than BITS bits, one entry each, from index P on (over the dead entries)
+    uint32_t base = bi->code_end[BITS] >> SH;  // P: the first prefix no code of at most BITS bits owns
+#pragma unroll
+    for (int l = BITS + 1; l <= kMaxCodeLen; ++l) {
+      const uint32_t nl = (bi->code_end[l] - bi->code_end[l - 1]) >> (kMaxCodeLen - l);
+      for (uint32_t j = tid; j < nl; j += nthreads) {
+        const uint32_t idx = bi->first_idx[l] + j;
+        T[base + j] = (idx < bi->num_syms ? syms[idx] : 0u) | ((uint32_t)l << 24) | (1u << 30);
+      }
+      base += nl;
     }
     __syncthreads();
   }
 }
 
-constexpr int kDecBits = 11;
-constexpr int kDecEntries = (1 << kDecBits) + 128;  // 11-bit part + one entry per 12-bit code beyond the first 2048 - P (at most 256 of them)
+// 2^bits entries + what the longer codes add beyond the dead prefixes they replace (see
+// build_dtable): at most 256 codes in all; with 11 bits every dead prefix holds exactly two
+__host__ __device__ constexpr int dec_entries(int bits) { return (1 << bits) + (bits == 11 ? 128 : 256); }
+// Index bits of the decode table.  A bigger table yields more symbols per lookup but costs 2^bits
+// entries to build per block and shared memory that could hold more resident streams: the best
+// size grows with the block and with the streams that share a table (measured on the K x block
+// grid of BASELINE config 5, profiles/r2_decode_table_bits.md).
+inline int dec_bits_for(int K, uint32_t block_size) {
+  static const int forced = [] {  // tuning aid: HUFB200_DEC_BITS=9|10|11 overrides the choice
+    const char* e = getenv("HUFB200_DEC_BITS");
+    const int v = e ? atoi(e) : 0;
+    return v >= 9 && v <= 11 ? v : 0;
+  }();
+  if (forced) return forced;
+  if (block_size <= (32u << 10)) return 9;
+  if (block_size <= (64u << 10)) return K <= 16 ? 9 : 10;
+  if (block_size <= (128u << 10)) return 10;
+  if (block_size <= (256u << 10)) return (K > 16 && K <= 40) ? 11 : 10;
+  return 11;
+}
 #ifndef HUF_DEC_LOOKUPS
 #define HUF_DEC_LOOKUPS 10
 #endif
@@ -1261,24 +1287,26 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 }
 
 // per-CTA scratch behind the tables: the T1 build scratch, later the lane rings and output rows
-__host__ __device__ inline size_t dec_region_bytes(int bpc, int nthreads) {
-  const size_t a = (size_t)bpc * kDecEntries;
+__host__ __device__ inline size_t dec_region_bytes(int bpc, int nthreads, int entries) {
+  const size_t a = (size_t)bpc * entries;
   const size_t b = (size_t)(nthreads >> 5) * 16 * 32 * 4 + (((size_t)nthreads * kDecRow + 15) & ~(size_t)15);
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
+template <int kDecBits>
 __global__ void __launch_bounds__(kDecMaxThreads)
 k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* __restrict__ offsets,
                     const uint32_t* __restrict__ comp_sizes, uint32_t n_blocks, int K, int bpc,
                     uint8_t* __restrict__ raw, uint64_t raw_n, uint32_t block_size,
                     uint32_t* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t dsm[];
-  // layout: tables [bpc][2048] u32 | region (T1 scratch, then rings [nwarps][16][32] u32 + rows) | infos [bpc]
+  constexpr int kDecEntries = dec_entries(kDecBits);
+  // layout: tables [bpc][kDecEntries] u32 | region (T1 scratch, then rings [nwarps][16][32] u32 + rows) | infos [bpc]
   const int nthreads = blockDim.x;
   const int nwarps = nthreads >> 5;
   uint32_t* tables = reinterpret_cast<uint32_t*>(dsm);
   uint8_t* region = dsm + (size_t)bpc * kDecEntries * 4;
-  DecBlockInfo* infos = reinterpret_cast<DecBlockInfo*>(region + dec_region_bytes(bpc, nthreads));
+  DecBlockInfo* infos = reinterpret_cast<DecBlockInfo*>(region + dec_region_bytes(bpc, nthreads, kDecEntries));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -1364,14 +1392,26 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
 
   // shared-space addresses, kept in registers
   const uint32_t t_addr = smem_u32(tables + (size_t)(lb < bpc ? lb : 0) * kDecEntries);
-  // base of the 12-bit-granular view: entry (p12 - P); inactive lanes look at entry max(p11, p12)
-  const uint32_t t12_addr = t_addr - 4u * (active ? (bi->code_end[kMaxCodeLen - 1] >> 1) : 0u);
+  // bases of the finer levels (see build_dtable): level l reads entry p_l + c_l; lanes without a
+  // stream keep c_l = 0 (their window is zero)
+  uint32_t tl_addr[kMaxCodeLen - kDecBits];
+  {
+    uint32_t base = active ? (bi->code_end[kDecBits] >> (kMaxCodeLen - kDecBits)) : 0u;
+#pragma unroll
+    for (int l = kDecBits + 1; l <= kMaxCodeLen; ++l) {
+      const uint32_t first = active ? (bi->code_end[l - 1] >> (kMaxCodeLen - l)) : 0u;
+      tl_addr[l - kDecBits - 1] = t_addr + 4u * (base - first);
+      if (active) base += (bi->code_end[l] - bi->code_end[l - 1]) >> (kMaxCodeLen - l);
+    }
+  }
   const uint32_t col = smem_u32(region) + (uint32_t)warp * (16 * 32 * 4) + 4u * (uint32_t)lane;  // word i at col + (i & 15) * 128
   // output staging ring: word j (4 symbols) of this lane at row + (j & 15) * 128 -- lane-private bank
   const uint32_t row = smem_u32(region) + (uint32_t)nwarps * (16 * 32 * 4) + (uint32_t)warp * (32 * kDecRow) + 4u * (uint32_t)lane;
   // make the three addresses opaque so that they stay in registers instead of being recomputed
   // from tid / %ctaid inside the lookup loop
-  asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(t12_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
+  asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
+#pragma unroll
+  for (int i = 0; i < kMaxCodeLen - kDecBits; ++i) asm volatile("" : "+r"(tl_addr[i]));
 
   // prime: stage two 32-byte sectors (the whole 16-word ring) and keep the next one in registers.
   // Each top-up takes a full sector, so the kernel does not depend on L1 to serve the other half
@@ -1424,10 +1464,13 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     for (int it = 0; it < kDecLookups; ++it) {
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
       const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
-      // index max(p11, p12 - P), formed on the byte addresses (see build_dtable)
-      // (signed max: t12_addr = t_addr - 4P may lie below zero as a shared-window offset)
-      uint32_t e = lds_u32_ro((uint32_t)max((int)entry_addr(t_addr, win >> (32 - kDecBits)),
-                                            (int)entry_addr(t12_addr, win >> (31 - kDecBits))));
+      // index = max over the levels, formed on the byte addresses (see build_dtable); signed: a
+      // level's base may lie below zero as a shared-window offset
+      int ea = (int)entry_addr(t_addr, win >> (32 - kDecBits));
+#pragma unroll
+      for (int l = kDecBits + 1; l <= kMaxCodeLen; ++l)
+        ea = max(ea, (int)entry_addr(tl_addr[l - kDecBits - 1], win >> (32 - l)));
+      uint32_t e = lds_u32_ro((uint32_t)ea);
       if (decltype(checked)::value && acc >= end_acc) e = 0;
       const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (position in the ring word being filled)
       const uint32_t old = acc;
@@ -1453,7 +1496,17 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t far_acc = end_acc >= ((3u * kDecLookups) << 6) ? end_acc - ((3u * kDecLookups) << 6) : 0u;
   const bool no_stream = !active || left == 0;
   const bool long_streams = __any_sync(0xffffffffu, left >= kPosWindow / 2 - 64);  // can a position reach the rebase point?
+  // Every lookup of an unfinished lane yields at least one symbol, so the warp needs at most
+  // max(left) / kDecLookups + 1 rounds; the count is enforced, so that no table or payload,
+  // however corrupt, can keep the kernel running.
+  uint32_t rounds_left = left / (uint32_t)kDecLookups + 4u;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) rounds_left = max(rounds_left, __shfl_xor_sync(0xffffffffu, rounds_left, d));
   while (__any_sync(0xffffffffu, acc < end_acc)) {
+    if (rounds_left-- == 0) {
+      if (status) atomicOr(status, 1u);
+      break;
+    }
     // rare (streams of more than 16 Mi symbols): move the position window.  Everything already
     // written out is dropped from the positions -- a multiple of the 64-byte ring, so ring
     // offsets keep their meaning -- and the window's end moves on by as much as is left.
@@ -1683,9 +1736,10 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
   return cudaGetLastError();
 }
 
-size_t decompress_smem_bytes(int K, int bpc) {
+size_t decompress_smem_bytes(int K, int bpc, uint32_t block_size) {
   const int nthreads = ((K * bpc + 31) / 32) * 32;
-  return (size_t)bpc * kDecEntries * 4 + dec_region_bytes(bpc, nthreads) + (size_t)bpc * sizeof(DecBlockInfo);
+  const int entries = dec_entries(dec_bits_for(K, block_size));
+  return (size_t)bpc * entries * 4 + dec_region_bytes(bpc, nthreads, entries) + (size_t)bpc * sizeof(DecBlockInfo);
 }
 
 cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
@@ -1693,26 +1747,27 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
                               uint64_t raw_n, uint32_t block_size, uint32_t* d_status, cudaStream_t st) {
   if (n_blocks == 0) return cudaSuccess;
   const int nthreads = ((K * bpc + 31) / 32) * 32;
-  const size_t smem = decompress_smem_bytes(K, bpc);
+  const int bits = dec_bits_for(K, block_size);
+  const size_t smem = decompress_smem_bytes(K, bpc, block_size);
+  auto kernel = bits == 9 ? k_decompress_blocks<9> : (bits == 10 ? k_decompress_blocks<10> : k_decompress_blocks<11>);
   {  // opt-in beyond the 48 KiB default: the attribute is per device and per kernel and shared by
      // all host threads, so it is set once per device, to the device's limit -- never per launch
      // (two threads decoding with different K would otherwise lower it under each other)
-    static std::atomic<unsigned long long> configured{0};
+    static std::atomic<unsigned long long> configured[3];
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull)) {
+    if (dev >= 64 || !((configured[bits - 9].load(std::memory_order_acquire) >> dev) & 1ull)) {
       int optin = 0;
       e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
       if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_decompress_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
       if (e != cudaSuccess) return e;
-      if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
+      if (dev < 64) configured[bits - 9].fetch_or(1ull << dev, std::memory_order_release);
     }
   }
   const uint32_t grid = (n_blocks + bpc - 1) / bpc;
-  k_decompress_blocks<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n,
-                                                    block_size, d_status);
+  kernel<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n, block_size, d_status);
   return cudaGetLastError();
 }
 

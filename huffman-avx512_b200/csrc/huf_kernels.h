@@ -22,7 +22,7 @@ constexpr int kCompWarps = kWorkThreads / 32;  // worker warps
 constexpr int kDecMaxThreads = 256;
 
 size_t table_bytes();
-size_t decompress_smem_bytes(int K, int bpc);
+size_t decompress_smem_bytes(int K, int bpc, uint32_t block_size);
 
 cudaError_t launch_histogram(const uint8_t* d_in, uint64_t n, unsigned long long* d_out, int grid,
                              cudaStream_t st);
