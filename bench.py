@@ -229,6 +229,96 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+# ----------------------------------------------------------------------------- config 1
+
+def config1_table(huf, seconds=0.25):
+    """BASELINE config 1, the reference's own benchmark unit (codec/huffman_benchmark.cpp:61-81): ONE
+    100 KiB biased buffer (GenerateProbaData(0.2, 102400), tests/golden/proba02_100k.bin) through
+    the single-buffer drop-in calls that HuffmanCompressorB200<K>::Compress / Decompress make
+    (hufb200_compress / hufb200_decompress, host pointers, copies and synchronisation inside), for
+    K in {4,8,16,32,48}: microseconds per call and MiB/s -- beside the reference's scalar / AVX-512
+    paths on the same buffer, one thread, its published method."""
+    import numpy as np
+    from _cases import golden
+    from _libs import Ref, have_ref
+    buf = np.frombuffer(golden("proba02_100k.bin"), dtype=np.uint8)
+    n = buf.size
+    L = huf.load()
+    out = {"buffer": "GenerateProbaData(0.2, 102400), 100 KiB", "unit": "MiB/s", "rows": {}}
+    cap = L.hufb200_compress_bound(n, 64) + 64
+    comp = np.empty(cap, dtype=np.uint8)
+    back = np.empty(n, dtype=np.uint8)
+    clen, olen = C.c_size_t(0), C.c_size_t(0)
+    for k in (4, 8, 16, 32, 48):
+        def cstep():
+            huf.binding.check(L.hufb200_compress(k, C.c_void_p(buf.ctypes.data), n, C.c_void_p(comp.ctypes.data), cap,
+                                                 C.byref(clen)))
+
+        def dstep():
+            huf.binding.check(L.hufb200_decompress(k, C.c_void_p(comp.ctypes.data), clen.value,
+                                                   C.c_void_p(back.ctypes.data), n, C.byref(olen)))
+        res = {}
+        for name, fn in (("compress", cstep), ("decompress", dstep)):
+            for _ in range(5):
+                fn()
+            t0 = time.perf_counter()
+            it = 0
+            while time.perf_counter() - t0 < seconds:
+                fn()
+                it += 1
+            us = (time.perf_counter() - t0) / it * 1e6
+            res[name + "_us_per_call"] = us
+            res[name + "_MiBps"] = n / (us * 1e-6) / 2 ** 20
+        assert olen.value == n and np.array_equal(back, buf), "config 1 round trip mismatch"
+        res["compressed_bytes"] = clen.value
+        out["rows"][f"HuffmanCompressorB200<{k}>"] = res
+    # one LARGE buffer through the same two calls (pinned host memory): compress spreads pieces of
+    # the K streams over the device; decompress has K serial streams and nothing finer to work on
+    import torch
+    from _cases import biased
+    nl = 64 << 20
+    big = torch.frombuffer(bytearray(biased(nl, seed=64)), dtype=torch.uint8).pin_memory()
+    capl = L.hufb200_compress_bound(nl, 32) + 64
+    compl = torch.empty(capl, dtype=torch.uint8).pin_memory()
+    backl = torch.empty(nl, dtype=torch.uint8).pin_memory()
+
+    def lc():
+        huf.binding.check(L.hufb200_compress(32, C.c_void_p(big.data_ptr()), nl, C.c_void_p(compl.data_ptr()), capl,
+                                             C.byref(clen)))
+
+    def ld():
+        huf.binding.check(L.hufb200_decompress(32, C.c_void_p(compl.data_ptr()), clen.value,
+                                               C.c_void_p(backl.data_ptr()), nl, C.byref(olen)))
+    tms = {}
+    for name, fn, reps in (("compress", lc, 5), ("decompress", ld, 2)):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        tms[name] = (time.perf_counter() - t0) / reps
+    assert olen.value == nl and torch.equal(backl, big), "large single buffer round trip mismatch"
+    out["single_buffer_64MiB_K32"] = {"host_memory": "pinned", "compress_ms": tms["compress"] * 1e3,
+                                      "compress_GBps": nl / tms["compress"] / GB, "decompress_ms": tms["decompress"] * 1e3,
+                                      "decompress_GBps": nl / tms["decompress"] / GB,
+                                      "note": "decompress of one buffer = 32 serial streams on 32 lanes; blocks are the scalable form"}
+    del big, compl, backl
+    if have_ref():
+        r = Ref()
+        flags = open("/proc/cpuinfo").read()
+        avx = all(f in flags for f in ("avx512f", "avx512bw", "avx512vbmi"))
+        for k in (4, 8, 16, 32, 48):
+            vs = [("HuffmanCompressorMulti", r.SCALAR)]
+            if avx and k % 8 == 0:
+                vs += [("HuffmanCompressorAvxGather", r.GATHER), ("HuffmanCompressorAvxPermute", r.PERMUTE)]
+            for cls, v in vs:
+                c, _ = r.bench(k, v, 0, buf, n, n, 1, 1, seconds)
+                d, _ = r.bench(k, v, 1, buf, n, n, 1, 1, seconds)
+                out["rows"][f"{cls}<{k}>"] = {"compress_MiBps": c / 2 ** 20, "decompress_MiBps": d / 2 ** 20,
+                                              "compress_us_per_call": n / c * 1e6, "decompress_us_per_call": n / d * 1e6,
+                                              "threads": 1}
+    return out
+
+
 # ----------------------------------------------------------------------------- parity sample
 
 def parity_sample(args, huf, codec, raw, slots, sizes, status, sh_table):
@@ -616,6 +706,7 @@ def run_ours(args):
             # produced, byte for byte against the CPU implementation (per-block tables), and the
             # same for shared-table mode against compress-with-that-table
             res["cpu_baseline"]["parity"] = parity_sample(args, huf, codec, raw, slots, sizes, status, sh_table)
+            res["cpu_baseline"]["config1"] = config1_table(huf)
         print(json.dumps(res))
     if world > 1:
         dist.barrier()

@@ -268,6 +268,47 @@ int compress_host(int k, size_t block_size, const uint8_t* raw, size_t n, uint32
   return HUFB200_OK;
 }
 
+// A single buffer of at least this many bytes is spread over the whole device (per-stream
+// histograms, one plan, pieces of 3072 symbols: launch_compress_single); smaller ones go to one
+// CTA, which needs a single launch.
+#ifndef HUF_SINGLE_MULTI_MIN
+#define HUF_SINGLE_MULTI_MIN (256u << 10)
+#endif
+// (with 8 streams or fewer one CTA has idle warps: there the spread form wins from 64 KiB on,
+// measured on the 100 KiB buffer of BASELINE config 1)
+inline bool single_goes_wide(size_t n, int k) { return n >= HUF_SINGLE_MULTI_MIN || (k <= 8 && n >= (64u << 10)); }
+
+// compresses one host buffer into ws.out; *size = compressed size
+int compress_single_host(int k, const uint8_t* raw, size_t n, const void* d_table, uint32_t* size) {
+  Workspace& ws = g_ws;
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const size_t bound = hufb200_compress_bound(n, k) + 16;
+  const uint32_t pieces = single_piece_count((uint32_t)n, k);
+  CU(ws.in.reserve(n + 16));
+  CU(ws.out.reserve(bound));
+  const size_t hist_b = (size_t)k * 256 * sizeof(uint32_t), plan_b = (single_plan_bytes() + 255) & ~(size_t)255,
+               tab_b = (table_bytes() + 255) & ~(size_t)255;
+  CU(ws.sizes.reserve(hist_b + plan_b + tab_b + (size_t)pieces * 4 + 256));
+  uint8_t* m = ws.sizes.as<uint8_t>();
+  uint32_t* d_hist = reinterpret_cast<uint32_t*>(m);
+  void* d_plan = m + hist_b;
+  void* d_tab = m + hist_b + plan_b;
+  uint32_t* d_pieces = reinterpret_cast<uint32_t*>(m + hist_b + plan_b + tab_b);
+  CU(cudaMemcpyAsync(ws.in.p, raw, n, cudaMemcpyHostToDevice, ws.st));
+  CU(cudaMemsetAsync(ws.out.p, 0, bound, ws.st));  // pieces OR their bits into it
+  CU(launch_compress_single(ws.in.as<uint8_t>(), (uint32_t)n, k, d_table, d_hist, d_tab, d_plan, d_pieces,
+                            ws.out.as<uint8_t>(), sms, ws.st));
+  g_launches.fetch_add(4, std::memory_order_relaxed);
+  uint32_t head[4] = {0, 0, 0, 0};  // total_size, hdr_total, bad
+  CU(cudaMemcpyAsync(head, d_plan, sizeof(head), cudaMemcpyDeviceToHost, ws.st));
+  CU(cudaStreamSynchronize(ws.st));
+  if (head[2]) return fail(HUFB200_E_CORRUPT, "a symbol of the input has no code in the supplied table");
+  *size = head[0];
+  return HUFB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -438,9 +479,15 @@ int hufb200_compress(int k, const uint8_t* raw, size_t n, uint8_t* out, size_t c
   if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
   if (n > kMaxBlock) return fail(HUFB200_E_INVALID, "n=%zu exceeds the 2^30 single-buffer limit", n);
   if (!out_len || (!raw && n) || (!out && cap)) return fail(HUFB200_E_INVALID, "null pointer");
-  std::vector<uint32_t> sizes;
+  std::vector<uint32_t> sizes(1);
   size_t stride = 0;
-  int rc = compress_host(k, n ? n : 1, raw, n, 1, nullptr, 0, &sizes, &stride);
+  int rc;
+  if (single_goes_wide(n, k)) {
+    CU(g_ws.ready());
+    rc = compress_single_host(k, raw, n, nullptr, &sizes[0]);
+  } else {
+    rc = compress_host(k, n ? n : 1, raw, n, 1, nullptr, 0, &sizes, &stride);
+  }
   if (rc) return rc;
   *out_len = sizes[0];
   if (sizes[0] > cap) return fail(HUFB200_E_NOSPACE, "need %u bytes, have %zu", sizes[0], cap);
@@ -466,9 +513,11 @@ int hufb200_compress_with_table(int k, const uint8_t* raw, size_t n, const uint1
   if (num_syms) CU(cudaMemcpyAsync(d_sy, sorted_syms, (size_t)num_syms, cudaMemcpyHostToDevice, ws.st));
   CU(launch_make_table(nullptr, reinterpret_cast<const uint16_t*>(d_lc), d_sy, num_syms, 1, ws.table.p, ws.st));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  std::vector<uint32_t> sizes;
+  std::vector<uint32_t> sizes(1);
   size_t stride = 0;
-  int rc = compress_host(k, n ? n : 1, raw, n, 1, ws.table.p, 1, &sizes, &stride);
+  int rc;
+  if (single_goes_wide(n, k)) rc = compress_single_host(k, raw, n, ws.table.p, &sizes[0]);
+  else rc = compress_host(k, n ? n : 1, raw, n, 1, ws.table.p, 1, &sizes, &stride);
   if (rc) return rc;
   *out_len = sizes[0];
   if (sizes[0] > cap) return fail(HUFB200_E_NOSPACE, "need %u bytes, have %zu", sizes[0], cap);

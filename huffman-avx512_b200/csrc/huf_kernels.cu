@@ -1625,6 +1625,253 @@ __global__ void __launch_bounds__(256) k_dump_dtable(const uint16_t* __restrict_
 }
 
 // ===========================================================================
+// One large buffer (CompressMulti<K> of a single string_view, codec/huffman.cpp:738-846) spread
+// over the whole device.  The format gives K streams and nothing finer, so the encoder makes its
+// own units: every stream is cut into pieces of kPieceSyms symbols.
+//   k_histogram_streams  per-stream histograms, as the reference takes them (:758-766)
+//   k_single_plan        total histogram -> table; stream bit totals = sum over symbols of
+//                        count x code length (:776-782); region ends; header; the plan
+//   k_piece_lengths      bit total of every piece (one warp per piece)
+//   k_encode_pieces      one warp per piece: its start bit is the sum of the pieces in front of
+//                        it; staged in shared memory like a block's stream and ORed into the
+//                        zero-filled output (pieces meet inside bytes)
+// ===========================================================================
+struct SinglePlan {
+  uint32_t total_size;           // size of the compressed buffer
+  uint32_t hdr_total;            // header incl. the end-offset table
+  uint32_t bad;                  // a symbol without a code (caller-supplied table)
+  uint32_t pad;
+  uint32_t region_end[kMaxK];    // cumulative, relative to hdr_total (:783-786)
+  uint32_t piece_first[kMaxK + 1];  // index of each stream's first piece
+};
+
+__host__ __device__ inline uint32_t pieces_of(uint32_t sz) { return (sz + kPieceSyms - 1) / kPieceSyms; }
+
+__global__ void __launch_bounds__(kHistThreads)
+k_histogram_streams(const uint8_t* __restrict__ in, uint32_t n, int K, uint32_t* __restrict__ hist /* [K][256] */) {
+  __shared__ uint32_t bins[256 * 32];
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) bins[i] = 0;
+  __syncthreads();
+  const uint32_t nvec_total = (n + 15) >> 4;
+  const uint32_t per = (nvec_total + gridDim.x - 1) / gridDim.x;
+  uint64_t pos = (uint64_t)blockIdx.x * per * 16;
+  uint64_t end = pos + (uint64_t)per * 16;
+  if (end > n) end = n;
+  const uint32_t q = n / (uint32_t)K, r = n % (uint32_t)K;
+  const uint64_t big = (uint64_t)r * (q + 1);  // the first r slices have q + 1 bytes (:98-108)
+  while (pos < end) {  // the CTA's share, slice by slice
+    uint32_t s;
+    uint64_t s_end;
+    if (pos < big) {
+      s = (uint32_t)(pos / (q + 1));
+      s_end = (uint64_t)(s + 1) * (q + 1);
+    } else {
+      s = r + (uint32_t)((pos - big) / q);
+      s_end = big + (uint64_t)(s - r + 1) * q;
+    }
+    const uint64_t seg_end = s_end < end ? s_end : end;
+    bins_accumulate(bins, in + pos, seg_end - pos, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      const uint32_t c = bins_reduce_clear(bins, threadIdx.x);
+      if (c) atomicAdd(hist + (size_t)s * 256 + threadIdx.x, c);
+    }
+    __syncthreads();
+    pos = seg_end;
+  }
+}
+
+// Header prefix of a compressed buffer (:799-808): raw size, length mask, counts, symbols.
+__device__ inline void write_header_prefix(const HufTable& tab, uint32_t raw_size, uint8_t* dst, int tid, int nthreads) {
+  const uint32_t hdr = tab.hdr_len;
+  const uint32_t mask = tab.len_mask;
+  const uint32_t npop = (uint32_t)__popc(mask);
+  for (uint32_t i = tid; i < hdr; i += nthreads) {
+    uint8_t v;
+    if (i < 4) v = (uint8_t)(raw_size >> (8 * i));
+    else if (i < 8) v = (uint8_t)(mask >> (8 * (i - 4)));
+    else if (i < 8 + npop) {
+      int bit = 0;  // position of the (i-8)-th set bit of the mask
+      for (uint32_t seen = 0;; ++bit)
+        if ((mask >> bit) & 1u) {
+          if (seen == i - 8) break;
+          ++seen;
+        }
+      v = (uint8_t)tab.len_count[bit];  // 256 wraps to 0 (:804)
+    } else v = tab.sorted_syms[i - 8 - npop];
+    dst[i] = v;
+  }
+}
+
+// One CTA of 256 threads.  shared_tab: nullptr = build the table from the total histogram.
+__global__ void __launch_bounds__(256) k_single_plan(const uint32_t* __restrict__ hist, uint32_t n, int K,
+                                                     const HufTable* __restrict__ shared_tab,
+                                                     HufTable* __restrict__ tab_out, SinglePlan* __restrict__ plan,
+                                                     uint8_t* __restrict__ dst) {
+  __shared__ HufTable tab;
+  __shared__ TableScratch sc;
+  __shared__ uint32_t tot[256];
+  __shared__ unsigned long long sbits[kMaxK];
+  __shared__ uint32_t bad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) bad = 0;
+  {
+    uint32_t t = 0;
+    for (int s = 0; s < K; ++s) t += hist[(size_t)s * 256 + tid];
+    tot[tid] = t;
+  }
+  __syncthreads();
+  if (shared_tab) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(shared_tab);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&tab);
+    for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += 256) d[i] = src[i];
+  } else if (warp == 0) {
+    if (n < (1u << 24)) build_table_warp<uint32_t, uint32_t>(tot, &tab, &sc);
+    else build_table_warp<uint32_t, unsigned long long>(tot, &tab, &sc);
+  }
+  __syncthreads();
+  if (tot[tid] != 0 && tab.enc[tid] == kEncInvalid) atomicOr(&bad, 1u);  // only possible with a supplied table
+  // stream bit totals (:776-782)
+  for (int s = warp; s < K; s += 8) {
+    unsigned long long b = 0;
+    for (int c = lane; c < 256; c += 32) {
+      const uint32_t e = tab.enc[c];
+      if (e != kEncInvalid) b += (unsigned long long)hist[(size_t)s * 256 + c] * (e >> 16);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(0xffffffffu, b, d);
+    if (lane == 0) sbits[s] = b;
+  }
+  __syncthreads();
+  const uint32_t hdr_total = tab.hdr_len + 4u * (uint32_t)(K - 1);
+  if (tid == 0) {
+    const uint32_t q = n / (uint32_t)K, r = n % (uint32_t)K;
+    uint32_t pos = 0, pc = 0;
+    for (int s = 0; s < K; ++s) {
+      pos += (uint32_t)((sbits[s] + 7) >> 3) + kSlop;
+      plan->region_end[s] = pos;
+      plan->piece_first[s] = pc;
+      pc += pieces_of(q + ((uint32_t)s < r ? 1u : 0u));
+    }
+    plan->piece_first[K] = pc;
+    plan->hdr_total = hdr_total;
+    plan->total_size = bad ? 0u : hdr_total + pos;
+    plan->bad = bad;
+  }
+  write_header_prefix(tab, n, dst, tid, 256);
+  __syncthreads();
+  for (int s = tid; s < K - 1; s += 256) {  // end_offset table (:809-811)
+    const uint32_t e = plan->region_end[s];
+    uint8_t* p = dst + tab.hdr_len + 4 * s;
+    p[0] = (uint8_t)e;
+    p[1] = (uint8_t)(e >> 8);
+    p[2] = (uint8_t)(e >> 16);
+    p[3] = (uint8_t)(e >> 24);
+  }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&tab);
+    uint32_t* d = reinterpret_cast<uint32_t*>(tab_out);
+    for (int i = tid; i < (int)(sizeof(HufTable) / 4); i += 256) d[i] = src[i];
+  }
+}
+
+// (stream, piece index inside the stream) of the global piece p; warp-uniform
+__device__ __forceinline__ void piece_of(const SinglePlan* plan, int K, uint32_t p, uint32_t& s, uint32_t& j) {
+  uint32_t lo = 0, hi = (uint32_t)K;  // piece_first[lo] <= p < piece_first[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (plan->piece_first[mid] <= p) lo = mid;
+    else hi = mid;
+  }
+  s = lo;
+  j = p - plan->piece_first[lo];
+}
+
+constexpr int kPieceWarps = 8;
+
+__global__ void __launch_bounds__(32 * kPieceWarps)
+k_piece_lengths(const uint8_t* __restrict__ raw, uint32_t n, int K, const HufTable* __restrict__ tab,
+                const SinglePlan* __restrict__ plan, uint32_t* __restrict__ piece_bits) {
+  __shared__ uint32_t enc[256];
+  __shared__ uint32_t bad;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) enc[i] = tab->enc[i];
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  const uint32_t p = blockIdx.x * kPieceWarps + (threadIdx.x >> 5);
+  if (p >= plan->piece_first[K]) return;
+  uint32_t s, j;
+  piece_of(plan, K, p, s, j);
+  uint32_t st, sz;
+  slice_geom(n, K, (int)s, st, sz);
+  const uint32_t off = j * kPieceSyms;
+  const uint32_t len = sz - off < kPieceSyms ? sz - off : kPieceSyms;
+  const unsigned long long b = stream_length_warp(enc, raw + st + off, len, &bad, raw + n);
+  if ((threadIdx.x & 31) == 0) piece_bits[p] = (uint32_t)b;
+}
+
+__global__ void __launch_bounds__(32 * kPieceWarps)
+k_encode_pieces(const uint8_t* __restrict__ raw, uint32_t n, int K, const HufTable* __restrict__ tab_g,
+                const SinglePlan* __restrict__ plan, const uint32_t* __restrict__ piece_bits,
+                uint8_t* __restrict__ dst) {
+  extern __shared__ __align__(1024) uint8_t esm[];
+  // layout: stage[kPieceWarps][kStageWords] u32 (each 1 KiB-aligned: 5 KiB) | HufTable
+  uint32_t* stage = reinterpret_cast<uint32_t*>(esm);
+  HufTable* tab = reinterpret_cast<HufTable*>(esm + (size_t)kPieceWarps * kStageWords * 4);
+  {
+    uint4* z = reinterpret_cast<uint4*>(esm);
+    for (int i = threadIdx.x; i < kPieceWarps * kStageWords / 4; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(tab_g);
+    uint32_t* d = reinterpret_cast<uint32_t*>(tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(HufTable) / 4); i += blockDim.x) d[i] = src[i];
+  }
+  __syncthreads();
+  if (plan->bad) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t p = blockIdx.x * kPieceWarps + warp;
+  if (p >= plan->piece_first[K]) return;
+  uint32_t s, j;
+  piece_of(plan, K, p, s, j);
+  uint32_t st, sz;
+  slice_geom(n, K, (int)s, st, sz);
+  const uint32_t off = j * kPieceSyms;
+  const uint32_t len = sz - off < kPieceSyms ? sz - off : kPieceSyms;
+  // start bit of the piece inside its stream
+  unsigned long long b0 = 0;
+  {
+    const uint32_t* pb = piece_bits + plan->piece_first[s];
+    for (uint32_t i = lane; i < j; i += 32) b0 += pb[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) b0 += __shfl_xor_sync(0xffffffffu, b0, d);
+  }
+  const uint32_t stage_base = smem_u32(stage + (size_t)warp * kStageWords);
+  bool over;
+  const uint32_t endbit = (uint32_t)encode_stream_staged_warp<true>(smem_u32(tab->enc), stage_base, raw + st + off, len,
+                                                                    &over, raw + n, (uint32_t)(b0 & 31u));
+  // Buffer word i is stream word m_base + i; output word m = top half of (W[m-1] : W[m]) << 8r
+  // (see copy_stream_out_warp) is linear in the stream's bits, so every piece ORs in what ITS
+  // bits contribute: words m_base .. m_base + nw (the last one only through W[m-1]).  The two
+  // words at either end may also get bits of the neighbouring pieces: atomics; the rest is ours.
+  const uint32_t e_off = plan->hdr_total + plan->region_end[s];
+  const uint32_t r = ((e_off - 1u) & 3u) + 1u;
+  const uint32_t sh = 8u * r;
+  uint32_t* wend = reinterpret_cast<uint32_t*>(dst + (e_off - r));
+  const uint32_t m_base = (uint32_t)(b0 >> 5);
+  const uint32_t nw = (endbit + 31u) >> 5;
+  const uint32_t sb = stage_base + 4u * kStageFront;
+  for (uint32_t i = lane; i <= nw; i += 32) {
+    const uint32_t lo = i < nw ? lds_u32(sb + 4u * i) : 0u;
+    const uint32_t hi = i >= 1 ? lds_u32(sb + 4u * (i - 1)) : 0u;
+    const uint32_t v = __funnelshift_lc(lo, hi, sh);
+    uint32_t* a = wend - (m_base + i);
+    if (i < 2 || i + 2 > nw) {
+      if (v) atomicOr(a, v);
+    } else {
+      *a = v;
+    }
+  }
+}
+
+// ===========================================================================
 // Slot layout -> packed layout
 // ===========================================================================
 __global__ void __launch_bounds__(1024) k_scan_sizes(const uint32_t* __restrict__ sizes, uint32_t n,
@@ -1736,19 +1983,25 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
   return cudaGetLastError();
 }
 
-size_t decompress_smem_bytes(int K, int bpc, uint32_t block_size) {
-  const int nthreads = ((K * bpc + 31) / 32) * 32;
+static size_t decompress_smem_bytes_threads(int bpc, int nthreads, int K, uint32_t block_size) {
   const int entries = dec_entries(dec_bits_for(K, block_size));
   return (size_t)bpc * entries * 4 + dec_region_bytes(bpc, nthreads, entries) + (size_t)bpc * sizeof(DecBlockInfo);
+}
+size_t decompress_smem_bytes(int K, int bpc, uint32_t block_size) {
+  return decompress_smem_bytes_threads(bpc, ((K * bpc + 31) / 32) * 32, K, block_size);
 }
 
 cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
                               const uint32_t* d_sizes, uint32_t n_blocks, int K, int bpc, uint8_t* d_raw,
                               uint64_t raw_n, uint32_t block_size, uint32_t* d_status, cudaStream_t st) {
   if (n_blocks == 0) return cudaSuccess;
-  const int nthreads = ((K * bpc + 31) / 32) * 32;
+  int nthreads = ((K * bpc + 31) / 32) * 32;
   const int bits = dec_bits_for(K, block_size);
-  const size_t smem = decompress_smem_bytes(K, bpc, block_size);
+  const uint32_t grid = (n_blocks + bpc - 1) / bpc;
+  // A launch that leaves most of the device empty (a single buffer, a few blocks) gets full-size
+  // CTAs: the extra warps have no stream, they only help build the tables and leave.
+  if (grid <= 64 && nthreads < kDecMaxThreads) nthreads = kDecMaxThreads;
+  const size_t smem = decompress_smem_bytes_threads(bpc, nthreads, K, block_size);
   auto kernel = bits == 9 ? k_decompress_blocks<9> : (bits == 10 ? k_decompress_blocks<10> : k_decompress_blocks<11>);
   {  // opt-in beyond the 48 KiB default: the attribute is per device and per kernel and shared by
      // all host threads, so it is set once per device, to the device's limit -- never per launch
@@ -1766,8 +2019,45 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
       if (dev < 64) configured[bits - 9].fetch_or(1ull << dev, std::memory_order_release);
     }
   }
-  const uint32_t grid = (n_blocks + bpc - 1) / bpc;
   kernel<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n, block_size, d_status);
+  return cudaGetLastError();
+}
+
+size_t single_plan_bytes() { return sizeof(SinglePlan); }
+
+uint32_t single_piece_count(uint32_t n, int K) {
+  const uint32_t q = n / (uint32_t)K, r = n % (uint32_t)K;
+  return r * pieces_of(q + 1) + ((uint32_t)K - r) * pieces_of(q);
+}
+
+// d_hist: K x 256 u32 (zeroed here), d_table_out: HufTable, d_plan: SinglePlan, d_piece_bits: one u32
+// per piece, d_out: zero-filled by the caller up to hufb200_compress_bound(n, K) + 8 bytes.
+cudaError_t launch_compress_single(const uint8_t* d_raw, uint32_t n, int K, const void* d_shared_table,
+                                   uint32_t* d_hist, void* d_table_out, void* d_plan, uint32_t* d_piece_bits,
+                                   uint8_t* d_out, int sms, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(d_hist, 0, (size_t)K * 256 * sizeof(uint32_t), st);
+  if (e != cudaSuccess) return e;
+  const uint32_t want = (n + 65535) / 65536;
+  const uint32_t grid = want < (uint32_t)sms * 4 ? (want ? want : 1) : (uint32_t)sms * 4;
+  k_histogram_streams<<<grid, kHistThreads, 0, st>>>(d_raw, n, K, d_hist);
+  k_single_plan<<<1, 256, 0, st>>>(d_hist, n, K, reinterpret_cast<const HufTable*>(d_shared_table),
+                                   reinterpret_cast<HufTable*>(d_table_out), reinterpret_cast<SinglePlan*>(d_plan), d_out);
+  const uint32_t pieces = single_piece_count(n, K);
+  const uint32_t pgrid = (pieces + kPieceWarps - 1) / kPieceWarps;
+  k_piece_lengths<<<pgrid, 32 * kPieceWarps, 0, st>>>(d_raw, n, K, reinterpret_cast<const HufTable*>(d_table_out),
+                                                      reinterpret_cast<const SinglePlan*>(d_plan), d_piece_bits);
+  const size_t smem = (size_t)kPieceWarps * kStageWords * 4 + sizeof(HufTable);
+  static std::atomic<unsigned long long> configured{0};
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull)) {
+    e = cudaFuncSetAttribute(k_encode_pieces, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
+  }
+  k_encode_pieces<<<pgrid, 32 * kPieceWarps, smem, st>>>(d_raw, n, K, reinterpret_cast<const HufTable*>(d_table_out),
+                                                         reinterpret_cast<const SinglePlan*>(d_plan), d_piece_bits, d_out);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,12 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
 cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
                               const uint32_t* d_sizes, uint32_t n_blocks, int K, int bpc, uint8_t* d_raw,
                               uint64_t raw_n, uint32_t block_size, uint32_t* d_status, cudaStream_t st);
+// One large buffer over the whole device (see huf_kernels.cu): five launches, no synchronisation.
+size_t single_plan_bytes();  // the plan starts with u32 total_size (0 = a symbol without a code), u32 hdr_total
+uint32_t single_piece_count(uint32_t n, int K);
+cudaError_t launch_compress_single(const uint8_t* d_raw, uint32_t n, int K, const void* d_shared_table,
+                                   uint32_t* d_hist, void* d_table_out, void* d_plan, uint32_t* d_piece_bits,
+                                   uint8_t* d_out, int sms, cudaStream_t st);
 cudaError_t launch_dump_dtable(const uint16_t* d_len_count, const uint8_t* d_syms, int num_syms, int one_symbol,
                                uint8_t* d_out, cudaStream_t st);
 cudaError_t launch_pack(const uint8_t* d_slots, uint64_t slot_stride, const uint32_t* d_sizes, uint32_t n_blocks,

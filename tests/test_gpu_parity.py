@@ -474,3 +474,36 @@ int main(int argc, char** argv) {
             assert blob[p + 4: p + 4 + n] == oracle.compress(k, d), (k, len(d))
             p += 4 + n
         assert p == len(blob)
+
+
+def test_large_single_buffer_spread_over_the_device(huf, oracle):
+    """hufb200_compress of ONE buffer of 256 KiB or more runs per-stream histograms, one plan and
+    pieces of 3072 symbols on many CTAs (launch_compress_single): the bytes must still be exactly
+    CompressMulti<K>'s -- ragged sizes, every K class, text and incompressible input, a supplied
+    table, and a supplied table that lacks a symbol."""
+    rng = np.random.default_rng(99)
+    cases = [
+        ("biased256k", biased(256 << 10, seed=1)),
+        ("biased1m+", biased((1 << 20) + 12345, seed=2)),
+        ("english3m", english(3_000_001, seed=3)),
+        ("uniform700k", bytes(rng.integers(0, 256, 700_003, dtype=np.uint8))),
+        ("single_symbol", b"z" * 400_000),
+        ("two_symbols", (b"ab" * 200_000) + b"a"),
+        ("long_codes", b"".join(bytes([65 + i]) * (1 << i) for i in range(19))),
+    ]
+    for name, data in cases:
+        for k in (1, 4, 8, 32, 48, 5):
+            want = oracle.compress(k, data)
+            got = huf.compress(k, data)
+            assert got == want, f"{name} K={k}: {len(got)} vs {len(want)} bytes"
+            assert huf.decompress(k, got) == data, (name, k)
+    data = biased(2_000_003, seed=8)
+    # a table that is not the buffer's own but has a code for each of its symbols
+    cd = oracle.make_coding(oracle.histogram(data) + 3 * oracle.histogram(english(500_000, seed=9)))
+    for k in (4, 32):
+        want = oracle.compress_with_table(k, data, cd["len_count"], cd["sorted_syms"])
+        assert huf.compress_with_table(k, data, cd["len_count"], cd["sorted_syms"]) == want
+    with pytest.raises(huf.HufError) as ei:
+        huf.compress_with_table(4, b"\xff" * 300_000, cd["len_count"], cd["sorted_syms"])
+    assert ei.value.code == -4
+    assert huf.decompress(32, huf.compress_with_table(32, data, cd["len_count"], cd["sorted_syms"])) == data

@@ -41,9 +41,20 @@ def main():
         cells += [(c["k"], c["block"], c["comp_GBps"] * 1e9, c["dec_GBps"] * 1e9) for c in sw.get("config5", [])
                   if c["block"] == bench["config"]["block_bytes"] and c["k"] != k]
     for kk, blk, c, d in sorted(cells):
-        rows.append(("B200 (1 GPU, device-resident)", kk, c, d, f"{blk >> 10} KiB blocks"))
-        gb.append({"name": f"BM_CompressBiased<::huffman::HuffmanCompressorB200<{kk}>>", "bytes_per_second": c})
-        gb.append({"name": f"BM_DecompressBiased<::huffman::HuffmanCompressorB200<{kk}>>", "bytes_per_second": d})
+        rows.append(("B200 (1 GPU, device-resident block container)", kk, c, d, f"{blk >> 10} KiB blocks"))
+        gb.append({"name": f"BM_CompressBiasedDeviceBlocks<::hufb200::BlockCodec<{kk}>>", "bytes_per_second": c})
+        gb.append({"name": f"BM_DecompressBiasedDeviceBlocks<::hufb200::BlockCodec<{kk}>>", "bytes_per_second": d})
+    # BASELINE config 1: the reference's own benchmark unit, one 100 KiB buffer per call
+    c1 = cpu.get("config1", {}).get("rows", {})
+    c1_rows = []
+    for name, r in c1.items():
+        cls = name if name.startswith("HuffmanCompressorB200") else name
+        ns = "::hufb200::" if name.startswith("HuffmanCompressorB200") else "::huffman::"
+        gb.append({"name": f"BM_CompressBiased<{ns}{cls}>", "bytes_per_second": r["compress_MiBps"] * 2 ** 20,
+                   "real_time": r["compress_us_per_call"], "time_unit": "us"})
+        gb.append({"name": f"BM_DecompressBiased<{ns}{cls}>", "bytes_per_second": r["decompress_MiBps"] * 2 ** 20,
+                   "real_time": r["decompress_us_per_call"], "time_unit": "us"})
+        c1_rows.append((name, r))
     rows.append(("Huff0", 4, None, None, cpu.get("huff0", "unavailable")))
     if args.json:
         json.dump({"context": {"source": args.bench_json, "metric": bench["metric"]}, "benchmarks": gb},
@@ -53,6 +64,15 @@ def main():
     print("-------|---|---|---|---")
     for m, s, c, d, w in rows:
         print(f"{m} | {s} | {mib(c)} | {mib(d)} | {w}")
+    if c1_rows:
+        print()
+        print("Config 1: ONE 100 KiB biased buffer per call (codec/huffman_benchmark.cpp:61-81), host pointers, one thread")
+        print()
+        print("Compressor | Compress | us/call | Decompress | us/call")
+        print("-----------|---|---|---|---")
+        for name, r in c1_rows:
+            print(f"{name} | {int(r['compress_MiBps'])} MiB/s | {r['compress_us_per_call']:.1f} | "
+                  f"{int(r['decompress_MiBps'])} MiB/s | {r['decompress_us_per_call']:.1f}")
 
 
 if __name__ == "__main__":
