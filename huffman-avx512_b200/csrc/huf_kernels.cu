@@ -3,11 +3,15 @@
 //   k_histogram          byte histogram, lane-privatised shared-memory bins, 128-bit loads
 //   k_build_table        canonical table from a 256 x u64 histogram (shared-table mode)
 //   k_make_table         same from a u32 histogram, dumping every field (ABI/table parity)
-//   k_compress_blocks    fused per-block histogram -> table -> encode (staged in shared memory; long
-//                        streams piecewise after a length pass); warp-specialised, blocks handed out dynamically
-//   k_decompress_blocks  header parse -> multi-symbol table (2 symbols x 12 bits = the reference's
-//                        Decoder2x; the kernel uses 3 symbols x 11 bits) -> one lane per stream decode
-//   k_dump_dtable        the decode kernel's table builder, for parity tests
+//   k_compress_blocks    fused per-block histogram -> table -> encode: warp-specialised CTA, blocks
+//                        handed out dynamically, streams drawn by ticket, staged in shared memory
+//                        and placed through an mbarrier chain (long streams piecewise after a length pass)
+//   k_decompress_blocks  header parse (validated) -> multi-symbol table with a 9/10/11-bit first
+//                        level and one entry per longer code -> one lane per stream decode
+//   k_dump_dtable        the decode kernel's table builder in the reference's formats
+//                        (Decoder1x, Decoder2x), for parity tests
+//   k_histogram_streams, k_single_plan, k_piece_lengths, k_encode_pieces
+//                        one large buffer spread over the device
 //   k_scan_sizes/k_pack  slot layout -> packed layout
 //
 // Reference behaviour: ahartik/huffman-avx512 codec/huffman.cpp, codec/histogram.cpp.
@@ -62,47 +66,8 @@ __device__ __forceinline__ uint32_t bins_reduce_clear(uint32_t* bins, int t) {
   return s;
 }
 
-// L2 eviction-priority hints (experiment HUF_L2HINT): a block is read twice by the compress
-// kernel -- first for its histogram (kept: evict_last), then for the encode (dropped: evict_first).
-#ifndef HUF_L2HINT
-#define HUF_L2HINT 0
-#endif
-#ifndef HUF_PREFETCH_L2
-#define HUF_PREFETCH_L2 0
-#endif
-__device__ __forceinline__ unsigned long long l2_policy_last() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned long long l2_policy_first() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-template <int kHint>  // 0 none, 1 evict_last, 2 evict_first
-__device__ __forceinline__ uint4 ldg128(const uint4* a) {
-  if (kHint == 0) return *a;
-  uint4 v;
-  const unsigned long long pol = kHint == 1 ? l2_policy_last() : l2_policy_first();
-  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(a), "l"(pol));
-  return v;
-}
-template <int kHint>
-__device__ __forceinline__ void stg32(uint32_t* a, uint32_t v) {
-  if (kHint == 0) {
-    *a = v;
-    return;
-  }
-  const unsigned long long pol = l2_policy_first();
-  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
-}
-
 // Accumulates the bytes [p, p+n) into the CTA's lane-private bins (all threads).
 // (t, nt): index of the calling thread among the nt threads that take part (whole warps).
-template <int kHint = 0>
 __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p, uint64_t n, uint32_t t, uint32_t nt) {
   uint32_t* bl = bins + lane_id();
   const uint64_t mis = (16 - ((uintptr_t)p & 15)) & 15;
@@ -113,12 +78,10 @@ __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p
   uint64_t i = t;
   const uint64_t step = nt;
   if (i + 3 * step < nvec) {  // batches of 4 loads per thread, the next batch in flight while one is counted
-    uint4 a = ldg128<kHint>(v + i), b = ldg128<kHint>(v + i + step), c = ldg128<kHint>(v + i + 2 * step),
-          d = ldg128<kHint>(v + i + 3 * step);
+    uint4 a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
     i += 4 * step;
     for (; i + 3 * step < nvec; i += 4 * step) {
-      const uint4 a2 = ldg128<kHint>(v + i), b2 = ldg128<kHint>(v + i + step), c2 = ldg128<kHint>(v + i + 2 * step),
-                  d2 = ldg128<kHint>(v + i + 3 * step);
+      const uint4 a2 = v[i], b2 = v[i + step], c2 = v[i + 2 * step], d2 = v[i + 3 * step];
       bins_add_vec(bl, a);
       bins_add_vec(bl, b);
       bins_add_vec(bl, c);
@@ -133,7 +96,7 @@ __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p
     bins_add_vec(bl, c);
     bins_add_vec(bl, d);
   }
-  for (; i < nvec; i += step) bins_add_vec(bl, ldg128<kHint>(v + i));
+  for (; i < nvec; i += step) bins_add_vec(bl, v[i]);
   const uint64_t done = head + (nvec << 4);
   for (uint64_t j = done + t; j < n; j += nt) atomicAdd(bl + ((uint32_t)p[j] << 5), 1u);
 }
@@ -630,7 +593,7 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
     constexpr bool kAligned = decltype(aligned_tag)::value;
     const uint8_t* p = sp + lane * 16;  // this lane's 16 symbols of the next group
     auto load = [&](const uint8_t* q) {
-      return kAligned ? ldg128<HUF_L2HINT ? 2 : 0>(reinterpret_cast<const uint4*>(q)) : load16(q, 0, 16, false, lim);
+      return kAligned ? *reinterpret_cast<const uint4*>(q) : load16(q, 0, 16, false, lim);
     };
     uint4 va = make_uint4(0, 0, 0, 0), vb = va;
     if (groups) va = load(p);
@@ -678,14 +641,14 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
   for (; rows >= 2; rows -= 2) {
     const uint32_t lo0 = lds_u32(sa), hi0 = lds_u32(sa - 4u);
     const uint32_t lo1 = lds_u32(sa + 128u), hi1 = lds_u32(sa + 124u);
-    stg32<HUF_L2HINT ? 2 : 0>(out, __funnelshift_lc(lo0, hi0, sh));
-    stg32<HUF_L2HINT ? 2 : 0>(out - 32, __funnelshift_lc(lo1, hi1, sh));
+    *out = __funnelshift_lc(lo0, hi0, sh);
+    *(out - 32) = __funnelshift_lc(lo1, hi1, sh);
     out -= 64;
     sa += 256;
   }
   if (rows) {
     const uint32_t lo0 = lds_u32(sa), hi0 = lds_u32(sa - 4u);
-    stg32<HUF_L2HINT ? 2 : 0>(out, __funnelshift_lc(lo0, hi0, sh));
+    *out = __funnelshift_lc(lo0, hi0, sh);
     out -= 32;
     sa += 128;
   }
@@ -986,11 +949,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
   // workers: histogram of block `blk` into sm.hist[slot]
   // (the union is all-zero on entry and left all-zero)
   auto histogram_block = [&](uint32_t blk, int slot) {
-#ifdef HUF_EXP_ALIAS  // tuning probe: every block reads the same few blocks, so the input stays in L2
-    bins_accumulate<0>(sm.u.bins, raw + (uint64_t)(blk % HUF_EXP_ALIAS) * block_size, block_len(blk), tid, kWorkThreads);
-#else
-    bins_accumulate<HUF_L2HINT ? 1 : 0>(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
-#endif
+    bins_accumulate(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
     worker_sync();
     if (tid < 256) sm.hist[slot][tid] = bins_reduce_clear(sm.u.bins, tid);  // one thread per bin
   };
@@ -1051,20 +1010,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
         if (!own_tables && check_presence) {  // every symbol of the block needs a code in the supplied table
           if (tid < 256 && sm.hist[cur][tid] != 0 && sm.tab[cur].enc[tid] == kEncInvalid) atomicOr(&sm.bad, 1u);
         }
-#ifdef HUF_EXP_ALIAS
-        const uint64_t boff = (uint64_t)(b % HUF_EXP_ALIAS) * block_size;
-#else
         const uint64_t boff = (uint64_t)b * block_size;
-#endif
-#if HUF_PREFETCH_L2
-        {  // the block was read for its histogram a whole block period ago and has left the L2 since:
-           // ask for it again, ahead of the encoder's loads (one 128-byte line per request)
-          const uint8_t* pb = raw + boff;
-          const uint32_t bl = block_len(b);
-          for (uint32_t o = (uint32_t)tid * 128u; o < bl; o += kWorkThreads * 128u)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
-        }
-#endif
         if (encode_block_workers<kLongSlices>(sm, sm.tab[cur], raw, n, raw + boff, block_len(b), block_size, K,
                                               out + (uint64_t)b * slot_stride, comp_sizes + b, status, staged_iter))
           ++staged_iter;
