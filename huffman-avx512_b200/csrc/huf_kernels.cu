@@ -481,33 +481,6 @@ __device__ __forceinline__ void stage_put64_start(uint32_t stream_base, uint32_t
   red_or_shared_off<8>(a, __funnelshift_r(0u, lo, pos));  // 0 for r == 0
 }
 
-// The puts of one lane's 16 symbols the general way: entries of HufTable::enc (code | len << 16),
-// pair and quad codes right-aligned, one put per quad (two for a quad longer than 32 bits).  Any
-// code lengths.  Out of line: the staged encoder below takes it, lane by lane, only when one of
-// the lane's quads is longer than 32 bits.  pos: stream bit position of the lane's first code.
-__device__ __noinline__ void put16_general(uint32_t enc_addr, uint32_t sb, uint32_t w0, uint32_t w1, uint32_t w2,
-                                           uint32_t w3, uint32_t valid, uint32_t pos) {
-  const uint32_t w[4] = {w0, w1, w2, w3};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t e[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      e[i] = (uint32_t)(4 * j + i) < valid ? lds_u32_ro(entry_addr(enc_addr, byte_of(w[j], i))) : 0u;
-      if (e[i] == kEncInvalid) e[i] = 0;  // no bits, as in enc2 (the stream is flagged by its entry sums)
-    }
-    uint32_t c01, l01, c23, l23;
-    quad_code<true>(e[0], e[1], e[2], e[3], c01, l01, c23, l23);
-    if (l01 + l23 <= 32) {
-      stage_put(sb, pos, (c01 << l23) | c23, l01 + l23);
-    } else {
-      stage_put(sb, pos, c01, l01);
-      stage_put(sb, pos + l01, c23, l23);
-    }
-    pos += l01 + l23;
-  }
-}
-
 // Staged mode, step 1: encode the whole stream into the warp's linear staging buffer (zeroed by
 // the previous copy-out).  Returns the stream's bit total (all ones if a symbol has no code);
 // *overflow is set when it does not fit (then only the count is valid and the caller falls back
@@ -525,9 +498,11 @@ __device__ __noinline__ void put16_general(uint32_t enc_addr, uint32_t sb, uint3
 //     quad has at most 32 bits;
 //   * two quads make a top-aligned 64-bit value that goes to the lane's scanned bit position with
 //     three red.shared.or (stage_put64_start).
-// A lane with a quad longer than 32 bits (rare) does its puts the general way (put16_general);
-// lengths and positions come from the entry sums either way.  A symbol without a code has an
-// enc2 entry of no bits and a marker bit that survives the sums: such a stream is reported.
+// A quad can have up to 48 bits: its low word (pair23 << (32 - len01), one more funnel shift) is
+// kept as well, and a lane with a quad longer than 32 bits puts its four quads one by one
+// instead of as two octets -- lengths and positions come from the entry sums either way.  A
+// symbol without a code has an enc2 entry of no bits and a marker bit that survives the sums:
+// such a stream is reported.
 template <bool kPiece = false>
 __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr, uint32_t stage_base,
                                                                const uint8_t* sp, uint32_t sz, bool* overflow,
@@ -543,7 +518,7 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   auto trip = [&](const uint4& v, auto full_tag, uint32_t valid) {
     constexpr bool kFull = decltype(full_tag)::value;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t Q[4], S[4];
+    uint32_t Q[4], Qlo[4], S[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t e[4];
@@ -554,6 +529,7 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
       const uint32_t p01 = (e[0] | __funnelshift_r(e[1], 0u, e[0])) & ~15u;
       const uint32_t p23 = (e[2] | __funnelshift_r(e[3], 0u, e[2])) & ~15u;
       Q[j] = p01 | __funnelshift_r(p23, 0u, s01);
+      Qlo[j] = __funnelshift_r(0u, p23, s01);  // bits 33.. of the quad; 0 unless it is longer than 32 bits
     }
     const uint32_t sA = S[0] + S[1], sB = S[2] + S[3];
     const uint32_t T = sA + sB;
@@ -574,7 +550,11 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
           if (h == 0) pos += sA & 0x7fu;
         }
       } else {
-        put16_general(enc_addr, sb, w[0], w[1], w[2], w[3], kFull ? 16u : valid, pos);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          stage_put64_start(sb, pos, Q[j], Qlo[j]);
+          pos += S[j] & 0x3fu;
+        }
       }
     }
     bitpos += total;
