@@ -514,16 +514,22 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   uint32_t flag = 0;  // OR of the entry sums: bits 12..16 set <=> some symbol had no code
   uint32_t sb = stage_base + 4u * kStageFront;  // stream word 0
   auto entry2 = [&](uint32_t w, int i) { return lds_u32_ro_enc2(entry_addr(enc_addr, byte_of(w, i))); };
+  // A trip in two halves, so that the registers holding its 16 symbols are free -- and the load
+  // of the trip after next can be issued into them -- before the long half starts.
   // kFull: every lane has 16 symbols; else `valid` of them (symbols past the slice's end contribute no bits)
-  auto trip = [&](const uint4& v, auto full_tag, uint32_t valid) {
+  auto gather = [&](const uint4& v, auto full_tag, uint32_t valid, uint32_t (&E)[16]) {
     constexpr bool kFull = decltype(full_tag)::value;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) E[4 * j + i] = (kFull || (uint32_t)(4 * j + i) < valid) ? entry2(w[j], i) : 0u;
+  };
+  auto finish = [&](const uint32_t (&E)[16]) {
     uint32_t Q[4], Qlo[4], S[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t e[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) e[i] = (kFull || (uint32_t)(4 * j + i) < valid) ? entry2(w[j], i) : 0u;
+      const uint32_t* e = &E[4 * j];
       const uint32_t s01 = e[0] + e[1];
       S[j] = s01 + (e[2] + e[3]);
       const uint32_t p01 = (e[0] | __funnelshift_r(e[1], 0u, e[0])) & ~15u;
@@ -560,10 +566,10 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
     bitpos += total;
   };
 
-  // full groups of 512 symbols: every lane has 16, nothing to mask; the next group's symbols are
-  // requested one trip ahead (two trips per iteration, so the two register sets just swap roles).
-  // The loop exists twice: slices that start on a 16-byte boundary (all shapes where K divides the
-  // block nicely) take plain 128-bit loads.
+  // full groups of 512 symbols: every lane has 16, nothing to mask; the symbols of the trip after
+  // next are requested as soon as a trip's lookups are issued (two trips per iteration, so the
+  // two register sets just swap roles).  The loop exists twice: slices that start on a 16-byte
+  // boundary (all shapes where K divides the block nicely) take plain 128-bit loads.
   uint32_t groups = sz >> 9;  // full groups still to do
   // keep the trip count and the shared-memory bases in registers: under the kernel's register
   // cap the compiler would otherwise re-derive them from the slice geometry and %warpid every trip
@@ -577,22 +583,31 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
     };
     uint4 va = make_uint4(0, 0, 0, 0), vb = va;
     if (groups) va = load(p);
+    if (groups >= 2) vb = load(p + 512);
+    uint32_t E[16];
     while (groups >= 2) {
-      vb = load(p + 512);
-      trip(va, std::true_type{}, 16);
+      gather(va, std::true_type{}, 16, E);
       if (groups > 2) va = load(p + 1024);
-      trip(vb, std::true_type{}, 16);
+      finish(E);
+      gather(vb, std::true_type{}, 16, E);
+      if (groups > 3) vb = load(p + 1536);
+      finish(E);
       p += 1024;
       groups -= 2;
     }
-    if (groups) trip(va, std::true_type{}, 16);
+    if (groups) {
+      gather(va, std::true_type{}, 16, E);
+      finish(E);
+    }
   };
   if (aligned) full_groups(std::true_type{});
   else full_groups(std::false_type{});
   // the slice's last, partial group
   if (sz & 511u) {
     const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
-    trip(load16(sp, off, valid, aligned, lim), std::false_type{}, valid);
+    uint32_t E[16];
+    gather(load16(sp, off, valid, aligned, lim), std::false_type{}, valid, E);
+    finish(E);
   }
   __syncwarp();
   *overflow = over;

@@ -130,6 +130,8 @@ def main():
                     help="config 4: total bytes over all GPUs (default: 2 GiB per GPU, i.e. 16 GiB on 8)")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "sweep.md"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--ks", default="", help="config 5: comma list of stream counts (default 4,8,16,32,48)")
+    ap.add_argument("--blocks-kib", default="", help="config 5: comma list of block sizes in KiB")
     ap.add_argument("--skip", default="", help="comma list of config3,config4,config5")
     args = ap.parse_args()
     huf = importlib.import_module("huffman-avx512_b200")
@@ -155,8 +157,10 @@ def main():
 
     if "config5" not in skip:
         raw = gen_biased(args.size, dev, 7 + 100 * RANK)
-        ks = (4, 8, 16, 32, 48)
+        ks = tuple(int(x) for x in args.ks.split(",")) if args.ks else (4, 8, 16, 32, 48)
         blocks = [16 << 10, 64 << 10, 128 << 10, 256 << 10, 1 << 20] if args.quick else [16 << 10, 32 << 10, 64 << 10, 128 << 10, 256 << 10, 512 << 10, 1 << 20]
+        if args.blocks_kib:
+            blocks = [int(x) << 10 for x in args.blocks_kib.split(",")]
         res["config5"] = []
         lines += [f"## Config 5: biased input, {args.size / (1 << 30):g} GiB per GPU, K x block size "
                   "(compress / decompress GB/s of raw bytes; roofline fraction)", "",
