@@ -46,6 +46,11 @@ ABI_SYMBOLS = [
     ("hufb200_decompress_blocks_dev", C.c_int,
      [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
       C.c_void_p, C.c_void_p]),
+    ("hufb200_decompress_split_work_bytes", C.c_size_t, [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t]),
+    ("hufb200_decompress_prefers_split", C.c_int, [C.c_int, C.c_size_t, C.c_size_t]),
+    ("hufb200_decompress_split_dev", C.c_int,
+     [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+      C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     ("hufb200_pack_blocks_dev", C.c_int,
      [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("hufb200_table_bytes", C.c_size_t, []),

@@ -200,6 +200,20 @@ constexpr size_t kContainerHeader = 32;
 #ifndef HUF_DEC_LANES
 #define HUF_DEC_LANES 64
 #endif
+// Split decode or one lane per stream?  The split path decodes every bit three times but on as
+// many lanes as the device holds; one lane per stream needs more than about 110 streams per SM (16384 in all) to be faster
+// (measured on the K x block grid, profiles/r2_split_decode.md).  HUFB200_SPLIT=0|1 forces it.
+bool prefer_split(int k, size_t n_blocks, size_t raw_n) {
+  static const int forced = [] {
+    const char* e = getenv("HUFB200_SPLIT");
+    return e ? (atoi(e) ? 1 : 0) : -1;
+  }();
+  if (raw_n == 0 || n_blocks == 0) return false;
+  if (forced >= 0) return forced == 1;
+  const size_t streams = n_blocks * (size_t)k;
+  return streams <= 16384 && raw_n / streams >= 4096;
+}
+
 int decode_bpc(int k) {
   static const int forced = [] {  // tuning aid: HUFB200_DEC_LANES overrides the lanes per decode CTA
     const char* e = getenv("HUFB200_DEC_LANES");
@@ -557,10 +571,24 @@ int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_
   } meta = {0ull, (uint32_t)n, 0u};
   CU(cudaMemcpyAsync(ws.misc.p, &meta, sizeof(meta), cudaMemcpyHostToDevice, ws.st));
   uint8_t* m = ws.misc.as<uint8_t>();
-  CU(launch_decompress(ws.in.as<uint8_t>(), reinterpret_cast<unsigned long long*>(m),
-                       reinterpret_cast<uint32_t*>(m + 8), 1, k, 1, ws.out.as<uint8_t>(), raw_size,
-                       (uint32_t)(raw_size ? raw_size : 1), reinterpret_cast<uint32_t*>(m + 12), ws.st));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (prefer_split(k, 1, raw_size)) {  // K streams cannot fill the device: cut them into items
+    int sms = 0;
+    rc = sm_count(&sms);
+    if (rc) return rc;
+    const uint32_t sub = split_sub_bits(raw_size, 1, k, sms);
+    CU(ws.offsets.reserve(decompress_split_work_bytes(1, k, (uint32_t)raw_size, sub)));
+    int launches = 0;
+    CU(launch_decompress_split(ws.in.as<uint8_t>(), reinterpret_cast<unsigned long long*>(m),
+                               reinterpret_cast<uint32_t*>(m + 8), 1, k, ws.out.as<uint8_t>(), raw_size,
+                               (uint32_t)raw_size, sub, ws.offsets.p, reinterpret_cast<uint32_t*>(m + 12), &launches,
+                               ws.st));
+    g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
+  } else {
+    CU(launch_decompress(ws.in.as<uint8_t>(), reinterpret_cast<unsigned long long*>(m),
+                         reinterpret_cast<uint32_t*>(m + 8), 1, k, 1, ws.out.as<uint8_t>(), raw_size,
+                         (uint32_t)(raw_size ? raw_size : 1), reinterpret_cast<uint32_t*>(m + 12), ws.st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   uint32_t status = 0;
   CU(cudaMemcpyAsync(&status, m + 12, 4, cudaMemcpyDeviceToHost, ws.st));
   if (raw_size) CU(cudaMemcpyAsync(out, ws.out.p, raw_size, cudaMemcpyDeviceToHost, ws.st));
@@ -746,8 +774,15 @@ int hufb200_decompress_blocks(const uint8_t* c, size_t n, uint8_t* out, size_t c
     CU(launch_scan_sizes(pp.sizes.as<uint32_t>(), (uint32_t)nblk, pp.offsets.as<unsigned long long>(), nullptr, pp.st));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     CU(cudaMemsetAsync(pp.misc.p, 0, 4, pp.st));
-    rc = hufb200_decompress_blocks_dev(k, bs, pp.in.as<uint8_t>(), pp.offsets.as<uint64_t>(), pp.sizes.as<uint32_t>(),
-                                       nblk, pp.out.as<uint8_t>(), rlen, pp.misc.as<uint32_t>(), pp.st);
+    if (prefer_split(k, nblk, rlen)) {
+      const size_t wb = hufb200_decompress_split_work_bytes(k, bs, nblk, rlen);
+      CU(pp.packed.reserve(wb));
+      rc = hufb200_decompress_split_dev(k, bs, pp.in.as<uint8_t>(), pp.offsets.as<uint64_t>(), pp.sizes.as<uint32_t>(),
+                                        nblk, pp.out.as<uint8_t>(), rlen, pp.packed.p, wb, pp.misc.as<uint32_t>(), pp.st);
+    } else {
+      rc = hufb200_decompress_blocks_dev(k, bs, pp.in.as<uint8_t>(), pp.offsets.as<uint64_t>(), pp.sizes.as<uint32_t>(),
+                                         nblk, pp.out.as<uint8_t>(), rlen, pp.misc.as<uint32_t>(), pp.st);
+    }
     if (rc) return rc;
     pp.meta[1] = 0;
     CU(cudaMemcpyAsync(&pp.meta[1], pp.misc.p, 4, cudaMemcpyDeviceToHost, pp.st));
@@ -792,6 +827,40 @@ int hufb200_decompress_blocks_dev(int k, size_t block_size, const uint8_t* d_com
                        (uint32_t)n_blocks, k, decode_bpc(k), d_raw, raw_n, (uint32_t)block_size, d_status,
                        (cudaStream_t)stream));
   if (n_blocks) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return HUFB200_OK;
+}
+
+size_t hufb200_decompress_split_work_bytes(int k, size_t block_size, size_t n_blocks, size_t raw_n) {
+  if (!valid_k(k) || block_size == 0 || block_size > kMaxBlock || (n_blocks >> 31)) return 0;
+  int sms = 0;
+  if (sm_count(&sms)) return 0;
+  return decompress_split_work_bytes((uint32_t)n_blocks, k, (uint32_t)block_size,
+                                     split_sub_bits(raw_n, (uint32_t)n_blocks, k, sms));
+}
+
+int hufb200_decompress_prefers_split(int k, size_t n_blocks, size_t raw_n) { return prefer_split(k, n_blocks, raw_n) ? 1 : 0; }
+
+int hufb200_decompress_split_dev(int k, size_t block_size, const uint8_t* d_comp, const uint64_t* d_offsets,
+                                 const uint32_t* d_comp_sizes, size_t n_blocks, uint8_t* d_raw, size_t raw_n,
+                                 void* d_work, size_t work_bytes, uint32_t* d_status, void* stream) {
+  if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
+  if (block_size == 0 || block_size > kMaxBlock) return fail(HUFB200_E_INVALID, "block_size outside 1..2^30");
+  if (n_blocks >> 31) return fail(HUFB200_E_INVALID, "too many blocks");
+  if (hufb200_blocks_count(raw_n, block_size) != n_blocks)
+    return fail(HUFB200_E_INVALID, "n_blocks does not match raw_n / block_size");
+  if (n_blocks && (!d_comp || !d_offsets || !d_comp_sizes || !d_raw || !d_work)) return fail(HUFB200_E_INVALID, "null pointer");
+  int sms = 0;
+  int rc = sm_count(&sms);
+  if (rc) return rc;
+  const uint32_t sub = split_sub_bits(raw_n, (uint32_t)n_blocks, k, sms);
+  const size_t need = decompress_split_work_bytes((uint32_t)n_blocks, k, (uint32_t)block_size, sub);
+  if (work_bytes < need) return fail(HUFB200_E_NOSPACE, "workspace: need %zu bytes, have %zu", need, work_bytes);
+  if (((uintptr_t)d_work & 255) != 0) return fail(HUFB200_E_INVALID, "d_work must be 256-byte aligned");
+  int launches = 0;
+  CU(launch_decompress_split(d_comp, reinterpret_cast<const unsigned long long*>(d_offsets), d_comp_sizes,
+                             (uint32_t)n_blocks, k, d_raw, raw_n, (uint32_t)block_size, sub, d_work, d_status, &launches,
+                             (cudaStream_t)stream));
+  g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
   return HUFB200_OK;
 }
 

@@ -1153,16 +1153,25 @@ static_assert(12 * kDecLookups + 31 < 6 * 32, "a round must not consume more tha
 constexpr uint32_t kRowWrap = (kDecRow / 4 - 1) * 128;
 constexpr int kDecEmits = (kDecChunk - 1 + 3 * kDecLookups) / kDecChunk;  // most complete chunks a round can leave behind
 
+// One thread.  The fixed part of the header is fetched with independent loads up front (a loop
+// that reads a count byte, then decides where the next one is, would chain up to 13 global-memory
+// latencies); the symbols are copied by the caller's threads (copy_header_syms) unless copy_syms.
 __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
-                                    DecBlockInfo* bi) {
+                                    DecBlockInfo* bi, bool copy_syms = true) {
   bi->ok = 0;
   bi->comp_size = comp_size;
+  bi->num_syms = 0;
   if (comp_size < 8u + 4u * (uint32_t)(K - 1)) return;
-  uint32_t raw_size = 0, mask = 0;
-  for (int i = 0; i < 4; ++i) {
-    raw_size |= (uint32_t)blk[i] << (8 * i);
-    mask |= (uint32_t)blk[4 + i] << (8 * i);
+  // raw_size, mask and the (at most 13) count bytes
+  unsigned long long f0 = 0, f1 = 0, f2 = 0;
+  const uint32_t avail = comp_size < 24u ? comp_size : 24u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f0 |= (unsigned long long)blk[i] << (8 * i);
+    if ((uint32_t)(8 + i) < avail) f1 |= (unsigned long long)blk[8 + i] << (8 * i);
+    if ((uint32_t)(16 + i) < avail) f2 |= (unsigned long long)blk[16 + i] << (8 * i);
   }
+  const uint32_t raw_size = (uint32_t)f0, mask = (uint32_t)(f0 >> 32);
   bi->raw_size = raw_size;
   if (mask >> (kMaxCodeLen + 1)) return;
   if (raw_size != expect_raw) return;
@@ -1172,7 +1181,9 @@ __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int 
   for (int l = 0; l <= kMaxCodeLen; ++l) {
     uint32_t cnt = 0;
     if (mask & (1u << l)) {
-      cnt = blk[pos++];
+      const uint32_t q = pos - 8u;  // < 13
+      cnt = (uint32_t)((q < 8u ? f1 >> (8u * q) : f2 >> (8u * (q - 8u))) & 0xffu);
+      ++pos;
       if (npop == 1 && cnt == 0) cnt = 256;  // :724-728
     }
     bi->first_idx[l] = nsyms;
@@ -1186,13 +1197,19 @@ __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int 
   // LimitCodeLengths keeps it so (:297-327), a lone symbol has the empty code (4096 >> 0).  An
   // over- or under-subscribed length table is corrupt; the decode table relies on completeness.
   if (nsyms != 0 && code != (1u << kMaxCodeLen)) return;
-  bi->num_syms = nsyms;
   bi->syms_off = pos;
   bi->ends_off = pos + nsyms;
   bi->payload_off = pos + nsyms + 4u * (uint32_t)(K - 1);
   if (bi->payload_off > comp_size) return;
-  for (uint32_t i = 0; i < nsyms; ++i) bi->syms[i] = blk[pos + i];
+  bi->num_syms = nsyms;
+  if (copy_syms)
+    for (uint32_t i = 0; i < nsyms; ++i) bi->syms[i] = blk[pos + i];
   bi->ok = 1;
+}
+// sorted_syms of a parsed header into bi->syms, by `nthreads` threads (bi->num_syms is 0 for a malformed header)
+__device__ __forceinline__ void copy_header_syms(const uint8_t* blk, DecBlockInfo* bi, int tid, int nthreads) {
+  const uint32_t n = bi->num_syms, off = bi->syms_off;
+  for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)nthreads) bi->syms[i] = blk[off + i];
 }
 
 // 32 bytes per lane in one instruction (256-bit global accesses, sm_100+): a lane's sector or
@@ -1234,12 +1251,47 @@ __host__ __device__ inline size_t dec_region_bytes(int bpc, int nthreads, int en
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
-template <int kDecBits>
+// ---- split decode (see "Split decode" below): the streams of a block are cut into items of
+// sub_bits stream bits; an item is one lane's work.  Device workspace, laid out by split_layout().
+constexpr int kSplitThreads = 128;  // items per CTA (all of one block: they share its decode table)
+constexpr int kSplitBits = 10;      // index bits of the decode table the split kernels use
+struct SplitArgs {
+  uint32_t sub_bits;           // item length in stream bits (a multiple of 32)
+  uint32_t max_block_ctas;     // most CTAs a block may need (the arrays are sized for n_blocks times that)
+  unsigned long long* cta_first;   // [n_blocks] exclusive prefix sum of block_ctas
+  unsigned long long* total_ctas;  // [1]
+  uint32_t* block_ctas;        // [n_blocks] CTAs of kSplitThreads items the block takes (0: empty or malformed)
+  uint32_t* s_first;           // [n_blocks * K] first item of the stream, counted within its block
+  uint32_t* s_nitems;          // [n_blocks * K]
+  uint32_t* s_eoff;            // [n_blocks * K] end of the stream's region relative to the payload start
+  uint32_t* s_bits;            // [n_blocks * K] 8 * (region bytes - 8): upper bound of the stream's bits
+  uint32_t* start;             // [items] bit the item's decode starts on (final after k_split_scan)
+  uint32_t* cnt;               // [items] symbols the item yields (final after k_split_scan)
+  uint32_t* exit_bit[2];       // [items] first code boundary at or behind the item's end; ping-pong over the passes
+  uint32_t* out_off;           // [items] offset of the item's first symbol within its slice
+};
+
+// The CTA's block in a launch whose CTAs are dealt out per block: the last b with cta_first[b] <= c
+// (blocks without CTAs share their successor's prefix value and are skipped by taking the last).
+__device__ __forceinline__ uint32_t split_block_of(const unsigned long long* cta_first, uint32_t n_blocks,
+                                                   unsigned long long c) {
+  uint32_t lo = 0, hi = n_blocks;  // invariant: cta_first[lo] <= c, cta_first[hi] > c (hi == n_blocks: total > c)
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (cta_first[mid] <= c) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// kItems: lane t decodes item t of the CTA's block (start bit, symbol count and output offset from
+// the workspace) instead of stream t % K from its first bit -- the write pass of the split decode.
+template <int kDecBits, bool kItems = false>
 __global__ void __launch_bounds__(kDecMaxThreads)
 k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* __restrict__ offsets,
                     const uint32_t* __restrict__ comp_sizes, uint32_t n_blocks, int K, int bpc,
                     uint8_t* __restrict__ raw, uint64_t raw_n, uint32_t block_size,
-                    uint32_t* __restrict__ status) {
+                    uint32_t* __restrict__ status, SplitArgs sa) {
   extern __shared__ __align__(16) uint8_t dsm[];
   constexpr int kDecEntries = dec_entries(kDecBits);
   // layout: tables [bpc][kDecEntries] u32 | region (T1 scratch, then rings [nwarps][16][32] u32 + rows) | infos [bpc]
@@ -1252,7 +1304,17 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const uint32_t b0 = blockIdx.x * (uint32_t)bpc;
+  uint32_t b0 = blockIdx.x * (uint32_t)bpc;
+  uint32_t item0 = 0;  // kItems: first item of this CTA within its block
+  unsigned long long gitem0 = 0;  // ... and in the workspace arrays
+  if constexpr (kItems) {  // bpc == 1, blockDim.x == kSplitThreads
+    const unsigned long long c = blockIdx.x;
+    if (c >= *sa.total_ctas) return;
+    b0 = split_block_of(sa.cta_first, n_blocks, c);
+    const unsigned long long first = sa.cta_first[b0];
+    item0 = (uint32_t)(c - first) * (uint32_t)kSplitThreads;
+    gitem0 = c * (unsigned long long)kSplitThreads;
+  }
 
   // ---- header parse, one thread per block
   if (tid < bpc) {
@@ -1262,10 +1324,15 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     if (b < n_blocks) {
       const uint64_t roff = (uint64_t)b * block_size;
       const uint32_t expect = (uint32_t)((raw_n - roff) < (uint64_t)block_size ? (raw_n - roff) : (uint64_t)block_size);
-      parse_header(comp + offsets[b], comp_sizes[b], K, expect, bi);
+      parse_header(comp + offsets[b], comp_sizes[b], K, expect, bi, false);
       if (!bi->ok && status) atomicOr(status, 1u);
+    } else {
+      bi->num_syms = 0;
     }
   }
+  __syncthreads();
+  for (int lb = 0; lb < bpc; ++lb)
+    if (b0 + lb < n_blocks) copy_header_syms(comp + offsets[b0 + lb], &infos[lb], tid, nthreads);
   __syncthreads();
   // ---- decode tables
   for (int lb = 0; lb < bpc; ++lb) {
@@ -1278,9 +1345,33 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   __syncthreads();
 
   // ---- decode: thread t <-> (local block t / K, stream t % K)
-  const int lb = tid / K;
-  const int s = tid - lb * K;
-  const uint32_t b = b0 + (uint32_t)lb;
+  int lb = tid / K;
+  int s = tid - lb * K;
+  uint32_t it_start = 0, it_cnt = 0, it_off = 0;
+  if constexpr (kItems) {  // thread t <-> item item0 + t of the block: find its stream
+    __shared__ uint32_t sf[kMaxK], sn[kMaxK];
+    if (tid < K) {
+      sf[tid] = sa.s_first[(size_t)b0 * K + tid];
+      sn[tid] = sa.s_nitems[(size_t)b0 * K + tid];
+    }
+    __syncthreads();
+    lb = bpc;  // no stream unless found below
+    s = 0;
+    const uint32_t li = item0 + (uint32_t)tid;
+    for (int q = 0; q < K; ++q)
+      if (li >= sf[q] && li - sf[q] < sn[q]) {
+        lb = 0;
+        s = q;
+      }
+    if (lb == 0) {
+      const unsigned long long gi = gitem0 + (unsigned long long)tid;
+      it_start = sa.start[gi];
+      it_cnt = sa.cnt[gi];
+      it_off = sa.out_off[gi];
+      if (it_cnt == 0) lb = bpc;
+    }
+  }
+  const uint32_t b = b0 + (uint32_t)(kItems ? 0 : lb);
   bool active = (lb < bpc) && (b < n_blocks);
   const DecBlockInfo* bi = &infos[active ? lb : 0];
   active = active && bi->ok && bi->raw_size != 0;
@@ -1316,17 +1407,23 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       sz = 0;
       e_off = 0;
       e_prev = 0;
+      it_cnt = 0;
     }
     region_bytes = e_off - e_prev;
     pad_bits = 0;
     left = sz;
     outp = raw + (uint64_t)b * block_size + st;
-    const uintptr_t end_addr = (uintptr_t)(blk + bi->payload_off) + e_off;  // exclusive
+    uintptr_t end_addr = (uintptr_t)(blk + bi->payload_off) + e_off;  // exclusive
+    if constexpr (kItems) {  // the item's first bit is bit 7 - (start % 8) of the byte start / 8 below the region's end
+      left = it_cnt <= sz - (it_off < sz ? it_off : sz) ? it_cnt : 0u;  // (k_split_scan keeps the items inside the slice)
+      outp += it_off;
+      end_addr -= it_start >> 3;
+    }
     e16 = (end_addr + 31) & ~(uintptr_t)31;  // input is fetched in whole 32-byte sectors
     const uint32_t pad = (uint32_t)(e16 - end_addr);
     lo_lim = (uintptr_t)blk & ~(uintptr_t)31;
     rd = pad >> 2;
-    acc = 8 * (pad & 3);
+    acc = 8 * (pad & 3) + (kItems ? (it_start & 7u) : 0u);
     pad_bits = 8 * pad;
   }
   if (bad_lane && status) atomicOr(status, 1u);
@@ -1514,13 +1611,321 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // Position = 32 * (ring words behind the window) + bits consumed from the window.  The last
   // lookup may have decoded up to two symbols more than the slice has (from the zero padding
   // behind the stream; they are not written): each of them accounts for at most 12 bits more.
-  if (active && !bad_lane) {
+  if (!kItems && active && !bad_lane) {  // (items: k_split_scan has checked the stream's symbol count)
     const uint32_t consumed = 32u * (rd - 2u) + (acc & 63u) - pad_bits;
     const uint32_t extra = left ? (acc >> 6) - end_pos : 0u;  // 0..2 symbols past the slice's end
     const uint32_t stream_bits_max = 8u * (region_bytes - (uint32_t)kSlop);
     const bool ok = consumed + 7u >= stream_bits_max && consumed <= stream_bits_max + (uint32_t)kMaxCodeLen * extra &&
                     extra <= 2u;
     if (!ok && status) atomicOr(status, 1u);
+  }
+}
+
+// ===========================================================================
+// Split decode: more lanes than streams.  DecompressMulti<K> (codec/huffman.cpp:892-955) walks K
+// streams, and a Huffman stream can only be read from a code boundary -- but prefix codes
+// re-synchronise: a decoder started on an arbitrary bit falls into step with the true code
+// boundaries after a few codes.  So every stream is cut into items of sub_bits bits; a lane decodes
+// from its item's start to the first code boundary at or behind the item's end (its exit) and
+// counts the symbols on the way:
+//   k_split_plan   per block: header geometry -> items per stream, CTAs per block
+//   k_split_sync   pass 0: a short warm-up decode in front of every item gives its probable start,
+//                  from which it decodes to its exit and counts;
+//                  pass p: an item whose predecessor's exit differs from the start it used decodes
+//                  again from there (a warm-up that had not fallen into step yet).
+//   k_split_scan   per stream: the items are consistent up to the first one whose start is not its
+//                  predecessor's exit; offsets = prefix sums of the counts; what lies behind an
+//                  inconsistent item (codes that never re-synchronise, e.g. all of one length)
+//                  becomes ONE item that runs to the stream's end, so the result never depends on
+//                  re-synchronisation, only the speed does.  The symbol total is checked against
+//                  the slice (only the last item may over-count, by what the < 8 pad bits decode to).
+//   k_decompress_blocks<.., true>   the write pass: one lane per item.
+// Two decodes of every bit instead of one, on as many lanes as the device holds: it pays when the
+// streams are too few to fill the device (one buffer of K streams: K lanes otherwise).
+// ===========================================================================
+// One warp per block: lane 0 parses the header, the lanes take the streams.
+__global__ void __launch_bounds__(32)
+k_split_plan(const uint8_t* __restrict__ comp, const unsigned long long* __restrict__ offsets,
+             const uint32_t* __restrict__ comp_sizes, uint32_t n_blocks, int K, uint64_t raw_n, uint32_t block_size,
+             SplitArgs sa, uint32_t* __restrict__ status) {
+  __shared__ DecBlockInfo info;
+  const uint32_t b = blockIdx.x;
+  const int lane = threadIdx.x;
+  DecBlockInfo* bi = &info;
+  const uint64_t roff = (uint64_t)b * block_size;
+  const uint32_t expect = (uint32_t)((raw_n - roff) < (uint64_t)block_size ? (raw_n - roff) : (uint64_t)block_size);
+  const uint8_t* blk = comp + offsets[b];
+  if (lane == 0) parse_header(blk, comp_sizes[b], K, expect, bi, false);
+  __syncwarp();
+  bool ok = bi->ok != 0;
+  uint32_t items = 0;
+  if (ok && bi->raw_size != 0) {
+    const uint32_t payload = bi->comp_size - bi->payload_off;
+    auto end_of = [&](int s) -> uint32_t {  // :901
+      if (s == K - 1) return payload;
+      const uint8_t* p = blk + bi->ends_off + 4 * s;
+      return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    };
+    for (int s0 = 0; s0 < K; s0 += 32) {
+      const int s = s0 + lane;
+      uint32_t n = 0, bits = 0, e_off = 0;
+      bool good = true;
+      if (s < K) {
+        e_off = end_of(s);
+        const uint32_t e_prev = s ? end_of(s - 1) : 0u;
+        good = !(e_off > payload || e_prev > e_off || e_off - e_prev < (uint32_t)kSlop);
+        if (good) {
+          bits = 8u * (e_off - e_prev - (uint32_t)kSlop);
+          n = (bits + sa.sub_bits - 1) / sa.sub_bits;
+          if (n == 0) n = 1;
+        }
+      }
+      if (!__all_sync(0xffffffffu, good)) ok = false;
+      const uint32_t incl = warp_incl_scan(n);
+      if (s < K) {
+        const size_t g = (size_t)b * K + s;
+        sa.s_first[g] = items + incl - n;
+        sa.s_nitems[g] = n;
+        sa.s_eoff[g] = e_off;
+        sa.s_bits[g] = bits;
+      }
+      items += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  uint32_t ctas = ok ? (items + kSplitThreads - 1) / kSplitThreads : 0u;
+  if (ctas > sa.max_block_ctas) {  // more compressed bytes than a block of this size can have
+    ok = false;
+    ctas = 0;
+  }
+  if (lane == 0) {
+    sa.block_ctas[b] = ctas;
+    if (!ok && status) atomicOr(status, 1u);
+  }
+}
+
+// The stream as 32-bit words from the region's end down, seen through an aligned window: virtual
+// word v is the aligned little-endian u32 at wend - 4 - 4v, virtual bit = 8 * pad + stream bit.
+struct SplitReader {
+  uintptr_t wend, lo_lim;
+  __device__ __forceinline__ uint32_t word(uint32_t v) const {
+    const uintptr_t a = wend - 4u - 4u * (uintptr_t)v;
+    return a >= lo_lim ? __ldg(reinterpret_cast<const uint32_t*>(a)) : 0u;
+  }
+};
+
+// Walks the codes of a stream from bit `pos` to the first code boundary at or behind bit `limit`;
+// returns that boundary and adds the number of codes passed to cnt.  T: the block's decode table
+// (build_dtable<BITS, 3, true>), c_l: its level bases.
+template <int BITS>
+__device__ __forceinline__ uint32_t split_walk(const uint32_t* T, const DecBlockInfo& bi, const int (&c_l)[kMaxCodeLen - BITS + 1],
+                                               const SplitReader& rd, uint32_t pad_bits, uint32_t pos, uint32_t limit,
+                                               uint32_t& cnt) {
+  if (pos >= limit) return pos;
+  uint32_t P = pad_bits + pos;  // virtual bit position
+  const uint32_t Plimit = pad_bits + limit;
+  uint32_t wi = P >> 5;
+  uint32_t hi = rd.word(wi), lo = rd.word(wi + 1);
+  // far from the end: whole table entries (up to three symbols); an entry never spans more than
+  // BITS bits and a longer code has an entry of its own, so 3 * 12 bits of margin keep every
+  // code that starts in front of the limit counted one by one below
+  const uint32_t Pfar = Plimit > 36u ? Plimit - 36u : 0u;
+  while (P < Pfar) {
+    const uint32_t win = __funnelshift_l(lo, hi, P);
+    int idx = (int)(win >> (32 - BITS));
+#pragma unroll
+    for (int l = BITS + 1; l <= kMaxCodeLen; ++l) idx = max(idx, (int)(win >> (32 - l)) + c_l[l - BITS - 1]);
+    const uint32_t e = T[idx];
+    P += (e >> 24) & 15u;
+    cnt += e >> 30;
+    if ((P >> 5) != wi) {
+      ++wi;
+      hi = lo;
+      lo = rd.word(wi + 1);
+    }
+  }
+  // near the end: one code at a time, its length by the canonical ranges (code_end is the
+  // left-aligned end of each length's range; the code is complete, so the walk ends by 12)
+  while (P < Plimit) {
+    const uint32_t v = __funnelshift_l(lo, hi, P) >> (32 - kMaxCodeLen);
+    uint32_t l = 1;
+    while (l < (uint32_t)kMaxCodeLen && v >= bi.code_end[l]) ++l;
+    P += l;
+    ++cnt;
+    if ((P >> 5) != wi) {
+      ++wi;
+      hi = lo;
+      lo = rd.word(wi + 1);
+    }
+  }
+  return P - pad_bits;
+}
+
+// pass 0: item j > 0 first runs a short warm-up: it decodes from `warm` bits in front of its first
+//         bit and takes the first code boundary at or behind that bit as its start -- the true one
+//         as soon as the warm-up has fallen into step (item 0 starts on bit 0).  Then it decodes
+//         from there to the first boundary at or behind its end (its exit) and counts its symbols.
+// pass p >= 1: an item whose predecessor's exit is not the start it used decodes again from there.
+template <int BITS>
+__global__ void __launch_bounds__(kSplitThreads)
+k_split_sync(const uint8_t* __restrict__ comp, const unsigned long long* __restrict__ offsets,
+             const uint32_t* __restrict__ comp_sizes, uint32_t n_blocks, int K, uint64_t raw_n, uint32_t block_size,
+             SplitArgs sa, int pass) {
+  constexpr int kEntries = dec_entries(BITS);
+  __shared__ uint32_t T[kEntries];
+  __shared__ __align__(16) uint8_t L1[kEntries];
+  __shared__ DecBlockInfo bi;
+  __shared__ uint32_t sf[kMaxK], sn[kMaxK];
+  const unsigned long long c = blockIdx.x;
+  if (c >= *sa.total_ctas) return;
+  const int tid = threadIdx.x;
+  const uint32_t b = split_block_of(sa.cta_first, n_blocks, c);
+  const uint32_t li = (uint32_t)(c - sa.cta_first[b]) * (uint32_t)kSplitThreads + (uint32_t)tid;
+  const unsigned long long gi = c * (unsigned long long)kSplitThreads + (unsigned long long)tid;
+  if (tid < K) {
+    sf[tid] = sa.s_first[(size_t)b * K + tid];
+    sn[tid] = sa.s_nitems[(size_t)b * K + tid];
+  }
+  __syncthreads();
+  // this lane's item: stream s, item j of it
+  int s = -1;
+  uint32_t j = 0;
+  for (int q = 0; q < K; ++q)
+    if (li >= sf[q] && li - sf[q] < sn[q]) {
+      s = q;
+      j = li - sf[q];
+    }
+  const bool active = s >= 0;
+  const uint32_t* exit_prev = (pass & 1) ? sa.exit_bit[0] : sa.exit_bit[1];
+  uint32_t* exit_cur = (pass & 1) ? sa.exit_bit[1] : sa.exit_bit[0];
+  uint32_t start = 0;
+  bool need = active;
+  if (active && pass != 0) {
+    start = j ? exit_prev[gi - 1] : 0u;
+    need = start != sa.start[gi];
+  }
+  if (!__syncthreads_or(need)) {  // nothing in this CTA moves: the exits carry over
+    if (active) exit_cur[gi] = exit_prev[gi];
+    return;
+  }
+  const uint8_t* blk = comp + offsets[b];
+  if (tid == 0) {
+    const uint64_t roff = (uint64_t)b * block_size;
+    const uint32_t expect = (uint32_t)((raw_n - roff) < (uint64_t)block_size ? (raw_n - roff) : (uint64_t)block_size);
+    parse_header(blk, comp_sizes[b], K, expect, &bi, false);  // valid: k_split_plan gave the block CTAs
+  }
+  __syncthreads();
+  copy_header_syms(blk, &bi, tid, kSplitThreads);
+  __syncthreads();
+  build_dtable<BITS, 3, true>(&bi, bi.syms, T, L1, tid, kSplitThreads);
+  if (!active) return;
+  if (!need) {
+    exit_cur[gi] = exit_prev[gi];
+    return;
+  }
+  const uint32_t bits_max = sa.s_bits[(size_t)b * K + s];
+  uint32_t limit = (j + 1) * sa.sub_bits;
+  if (limit > bits_max || j + 1 == sn[s]) limit = bits_max;
+  uint32_t pos = start, cnt = 0;
+  if (bi.code_end[0] == 0) {  // (a lone symbol has the empty code: no bits, nothing to walk)
+    const uintptr_t end_addr = (uintptr_t)(blk + bi.payload_off) + sa.s_eoff[(size_t)b * K + s];
+    SplitReader rd;
+    rd.wend = (end_addr + 3) & ~(uintptr_t)3;
+    rd.lo_lim = (uintptr_t)blk & ~(uintptr_t)3;
+    const uint32_t pad_bits = 8u * (uint32_t)(rd.wend - end_addr);
+    // level bases of the table extension (see build_dtable)
+    int c_l[kMaxCodeLen - BITS + 1];
+    {
+      uint32_t base = bi.code_end[BITS] >> (kMaxCodeLen - BITS);
+#pragma unroll
+      for (int l = BITS + 1; l <= kMaxCodeLen; ++l) {
+        const uint32_t first = bi.code_end[l - 1] >> (kMaxCodeLen - l);
+        c_l[l - BITS - 1] = (int)base - (int)first;
+        base += (bi.code_end[l] - bi.code_end[l - 1]) >> (kMaxCodeLen - l);
+      }
+    }
+    if (pass == 0 && j != 0) {  // warm-up
+      const uint32_t first_bit = j * sa.sub_bits;
+      const uint32_t warm = sa.sub_bits / 2 < 512u ? sa.sub_bits / 2 : 512u;
+      uint32_t dummy = 0;
+      start = split_walk<BITS>(T, bi, c_l, rd, pad_bits, first_bit - warm, first_bit, dummy);
+    }
+    pos = split_walk<BITS>(T, bi, c_l, rd, pad_bits, start, limit, cnt);
+  }
+  sa.start[gi] = start;
+  sa.cnt[gi] = cnt;
+  exit_cur[gi] = pos;
+}
+
+// One CTA per stream.  final_pass: the pass whose exits are current.
+__global__ void __launch_bounds__(256)
+k_split_scan(const uint8_t* __restrict__ comp, const unsigned long long* __restrict__ offsets, uint32_t n_blocks, int K,
+             uint64_t raw_n, uint32_t block_size, SplitArgs sa, int final_pass, uint32_t* __restrict__ status) {
+  __shared__ uint32_t jbad_s, warp_tot[8], running_s;
+  const uint32_t g = blockIdx.x;
+  const uint32_t b = g / (uint32_t)K, s = g % (uint32_t)K;
+  if (b >= n_blocks || sa.block_ctas[b] == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = sa.s_nitems[g];
+  const unsigned long long gi0 = sa.cta_first[b] * (unsigned long long)kSplitThreads + sa.s_first[g];
+  const uint32_t* ex = (final_pass & 1) ? sa.exit_bit[1] : sa.exit_bit[0];
+  const uint64_t roff = (uint64_t)b * block_size;
+  const uint32_t bn = (uint32_t)((raw_n - roff) < (uint64_t)block_size ? (raw_n - roff) : (uint64_t)block_size);
+  uint32_t st, sz;
+  slice_geom(bn, K, (int)s, st, sz);
+  // a lone symbol (empty code): the stream has no bits and one item, which yields the whole slice
+  const uint8_t* blk = comp + offsets[b];
+  const uint32_t mask = (uint32_t)blk[4] | ((uint32_t)blk[5] << 8) | ((uint32_t)blk[6] << 16) | ((uint32_t)blk[7] << 24);
+  const bool lone = (mask & 1u) != 0;
+  if (tid == 0) {
+    jbad_s = n;
+    running_s = 0;
+  }
+  __syncthreads();
+  // first item whose start is not its predecessor's exit (item 0 starts on bit 0 by construction)
+  for (uint32_t j = 1 + (uint32_t)tid; j < n; j += 256)
+    if (sa.start[gi0 + j] != ex[gi0 + j - 1]) atomicMin(&jbad_s, j);
+  __syncthreads();
+  const uint32_t jbad = jbad_s;
+  // offsets of the consistent items: exclusive prefix sums of their counts
+  for (uint32_t j0 = 0; j0 < jbad; j0 += 256) {
+    const uint32_t j = j0 + (uint32_t)tid;
+    const uint32_t c = j < jbad ? sa.cnt[gi0 + j] : 0u;
+    const uint32_t incl = warp_incl_scan(c);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t before = running_s;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (j < jbad) sa.out_off[gi0 + j] = before + incl - c;
+    __syncthreads();
+    if (tid == 255) running_s = before + incl;
+    __syncthreads();
+  }
+  const uint32_t counted = running_s;
+  bool bad = false;
+  if (jbad < n) {  // the rest of the stream as one item from the last good exit on
+    for (uint32_t j = jbad + 1 + (uint32_t)tid; j < n; j += 256) sa.cnt[gi0 + j] = 0;
+    if (tid == 0) {
+      if (counted > sz) bad = true;
+      sa.start[gi0 + jbad] = ex[gi0 + jbad - 1];
+      sa.cnt[gi0 + jbad] = bad ? 0u : sz - counted;
+      sa.out_off[gi0 + jbad] = bad ? 0u : counted;
+    }
+  } else if (tid == 0) {
+    // every item is in step.  Only the last one can have counted too much: the < 8 pad bits behind
+    // the stream decode to at most 7 symbols.
+    const uint32_t last = sa.cnt[gi0 + n - 1];
+    if (lone) {
+      sa.cnt[gi0] = sz;
+      sa.out_off[gi0] = 0;
+    } else if (counted < sz || counted - sz > 7u || counted - sz > last) {
+      bad = true;
+    } else {
+      sa.cnt[gi0 + n - 1] = last - (counted - sz);
+    }
+  }
+  if (bad) {  // malformed: the stream yields nothing, and the call reports it
+    for (uint32_t j = 0; j < n; ++j) sa.cnt[gi0 + j] = 0;
+    if (status) atomicOr(status, 1u);
   }
 }
 
@@ -1960,7 +2365,111 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
       if (dev < 64) configured[bits - 9].fetch_or(1ull << dev, std::memory_order_release);
     }
   }
-  kernel<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n, block_size, d_status);
+  kernel<<<grid, nthreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, bpc, d_raw, raw_n, block_size, d_status,
+                                       SplitArgs{});
+  return cudaGetLastError();
+}
+
+// ---- split decode: workspace layout and launches
+uint32_t split_sub_bits(uint64_t raw_n, uint32_t n_blocks, int K, int sms) {
+  // items of about (compressed bits) / (a quarter of the lanes the device holds), between 1024 and 8192 bits
+  (void)n_blocks;
+  (void)K;
+  static const uint32_t forced = [] {  // tuning / test aid: HUFB200_SPLIT_BITS=64..65536 fixes the item length
+    const char* e = getenv("HUFB200_SPLIT_BITS");
+    const int v = e ? atoi(e) : 0;
+    return v >= 64 && v <= 65536 ? (uint32_t)v : 0u;
+  }();
+  if (forced) return forced;
+  // (measured, profiles/r2_split_decode.md: 8192-bit items are as fast as any for a full device;
+  // a 64 MiB buffer does best with 4096, small buffers need every lane they can get)
+  const uint64_t lanes = (uint64_t)sms * 512u;
+  uint64_t want = raw_n * 4u / (lanes ? lanes : 1u);  // ~4 bits per symbol
+  uint32_t sub = 1024;
+  while (sub < 8192u && sub < want) sub <<= 1;
+  return sub;
+}
+static uint32_t split_max_block_ctas(uint32_t block_size, int K, uint32_t sub_bits) {
+  // no block has more compressed bytes than 12 bits per symbol plus the header and the slop
+  const uint64_t bound_bits = (uint64_t)block_size * kMaxCodeLen + 8u * (uint64_t)(8 + 13 + 256 + 4 * K + kSlop * K);
+  const uint64_t items = bound_bits / sub_bits + (uint64_t)K + 1u;
+  return (uint32_t)((items + kSplitThreads - 1) / kSplitThreads);
+}
+static SplitArgs split_layout(uint8_t* base, uint32_t n_blocks, int K, uint32_t block_size, uint32_t sub_bits,
+                              size_t* total) {
+  SplitArgs a{};
+  a.sub_bits = sub_bits;
+  a.max_block_ctas = split_max_block_ctas(block_size, K, sub_bits);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const size_t ns = (size_t)n_blocks * K;
+  const size_t items = (size_t)n_blocks * a.max_block_ctas * kSplitThreads;
+  a.cta_first = reinterpret_cast<unsigned long long*>(take(8 * ((size_t)n_blocks + 1)));
+  a.total_ctas = reinterpret_cast<unsigned long long*>(take(8));
+  a.block_ctas = reinterpret_cast<uint32_t*>(take(4 * (size_t)n_blocks));
+  a.s_first = reinterpret_cast<uint32_t*>(take(4 * ns));
+  a.s_nitems = reinterpret_cast<uint32_t*>(take(4 * ns));
+  a.s_eoff = reinterpret_cast<uint32_t*>(take(4 * ns));
+  a.s_bits = reinterpret_cast<uint32_t*>(take(4 * ns));
+  a.start = reinterpret_cast<uint32_t*>(take(4 * items));
+  a.cnt = reinterpret_cast<uint32_t*>(take(4 * items));
+  a.exit_bit[0] = reinterpret_cast<uint32_t*>(take(4 * items));
+  a.exit_bit[1] = reinterpret_cast<uint32_t*>(take(4 * items));
+  a.out_off = reinterpret_cast<uint32_t*>(take(4 * items));
+  *total = off;
+  return a;
+}
+size_t decompress_split_work_bytes(uint32_t n_blocks, int K, uint32_t block_size, uint32_t sub_bits) {
+  size_t total = 0;
+  split_layout(nullptr, n_blocks, K, block_size, sub_bits, &total);
+  return total;
+}
+
+constexpr int kSplitPasses = 3;  // pass 0 and two repairs; what is still out of step decodes serially (k_split_scan)
+
+cudaError_t launch_decompress_split(const uint8_t* d_comp, const unsigned long long* d_offsets,
+                                    const uint32_t* d_sizes, uint32_t n_blocks, int K, uint8_t* d_raw, uint64_t raw_n,
+                                    uint32_t block_size, uint32_t sub_bits, void* d_work, uint32_t* d_status,
+                                    int* launches, cudaStream_t st) {
+  *launches = 0;
+  if (n_blocks == 0) return cudaSuccess;
+  size_t total = 0;
+  const SplitArgs sa = split_layout(reinterpret_cast<uint8_t*>(d_work), n_blocks, K, block_size, sub_bits, &total);
+  const unsigned long long max_ctas = (unsigned long long)n_blocks * sa.max_block_ctas;
+  if (max_ctas >> 31) return cudaErrorInvalidValue;
+  k_split_plan<<<n_blocks, 32, 0, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, raw_n, block_size, sa, d_status);
+  k_scan_sizes<<<1, 1024, 0, st>>>(sa.block_ctas, n_blocks, sa.cta_first, sa.total_ctas);
+  for (int pass = 0; pass < kSplitPasses; ++pass)
+    k_split_sync<kSplitBits><<<(uint32_t)max_ctas, kSplitThreads, 0, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, raw_n,
+                                                                           block_size, sa, pass);
+  k_split_scan<<<n_blocks * (uint32_t)K, 256, 0, st>>>(d_comp, d_offsets, n_blocks, K, raw_n, block_size, sa,
+                                                        kSplitPasses - 1, d_status);
+  *launches = 3 + kSplitPasses;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // the write pass: the decode kernel with one lane per item
+  auto kernel = k_decompress_blocks<kSplitBits, true>;
+  const int entries = dec_entries(kSplitBits);
+  const size_t smem = (size_t)entries * 4 + dec_region_bytes(1, kSplitThreads, entries) + sizeof(DecBlockInfo);
+  {
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 64 || !((configured.load(std::memory_order_acquire) >> dev) & 1ull)) {
+      // (this instance always takes the same amount: one table of kSplitBits bits, kSplitThreads lanes)
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if (dev < 64) configured.fetch_or(1ull << dev, std::memory_order_release);
+    }
+  }
+  kernel<<<(uint32_t)max_ctas, kSplitThreads, smem, st>>>(d_comp, d_offsets, d_sizes, n_blocks, K, 1, d_raw, raw_n,
+                                                          block_size, d_status, sa);
+  *launches += 1;
   return cudaGetLastError();
 }
 

@@ -35,6 +35,15 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
 cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d_offsets,
                               const uint32_t* d_sizes, uint32_t n_blocks, int K, int bpc, uint8_t* d_raw,
                               uint64_t raw_n, uint32_t block_size, uint32_t* d_status, cudaStream_t st);
+// Split decode (streams cut into items of sub_bits bits, one lane per item; see huf_kernels.cu):
+// plan, scan, three sync passes, item scan, write pass -- no synchronisation.  d_work:
+// decompress_split_work_bytes() bytes.
+uint32_t split_sub_bits(uint64_t raw_n, uint32_t n_blocks, int K, int sms);
+size_t decompress_split_work_bytes(uint32_t n_blocks, int K, uint32_t block_size, uint32_t sub_bits);
+cudaError_t launch_decompress_split(const uint8_t* d_comp, const unsigned long long* d_offsets,
+                                    const uint32_t* d_sizes, uint32_t n_blocks, int K, uint8_t* d_raw, uint64_t raw_n,
+                                    uint32_t block_size, uint32_t sub_bits, void* d_work, uint32_t* d_status,
+                                    int* launches, cudaStream_t st);
 // One large buffer over the whole device (see huf_kernels.cu): five launches, no synchronisation.
 size_t single_plan_bytes();  // the plan starts with u32 total_size (0 = a symbol without a code), u32 hdr_total
 uint32_t single_piece_count(uint32_t n, int K);

@@ -91,13 +91,31 @@ class BlockCodec:
                                                  _ptr(packed), _ptr(offsets), _ptr(total), _stream()))
         return packed, offsets, total
 
-    def decompress(self, comp, offsets, sizes, raw_n, out=None, status=None):
-        """Decodes the blocks at comp[offsets[b] : offsets[b]+sizes[b]] into `raw_n` bytes."""
+    def decompress(self, comp, offsets, sizes, raw_n, out=None, status=None, split=None, work=None):
+        """Decodes the blocks at comp[offsets[b] : offsets[b]+sizes[b]] into `raw_n` bytes.
+        split: None = the library's choice (hufb200_decompress_prefers_split), True / False = the
+        split decode (streams cut into items, one lane per item) / one lane per stream.
+        work: workspace tensor for the split decode (split_work_bytes(raw_n) bytes), kept by the
+        caller across calls; allocated here when missing."""
         assert comp.is_cuda and comp.dtype == torch.uint8
         nb = self.n_blocks(raw_n)
         if out is None:
             out = torch.empty(max(raw_n, 1), dtype=torch.uint8, device=comp.device)
+        if split is None:
+            split = bool(self.L.hufb200_decompress_prefers_split(self.k, nb, raw_n))
         with torch.cuda.device(comp.device):
-            check(self.L.hufb200_decompress_blocks_dev(self.k, self.block_size, _ptr(comp), _ptr(offsets),
-                                                       _ptr(sizes), nb, _ptr(out), raw_n, _ptr(status), _stream()))
+            if split and nb:
+                need = self.split_work_bytes(raw_n)
+                if work is None or work.numel() < need:
+                    work = torch.empty(need, dtype=torch.uint8, device=comp.device)
+                check(self.L.hufb200_decompress_split_dev(self.k, self.block_size, _ptr(comp), _ptr(offsets),
+                                                          _ptr(sizes), nb, _ptr(out), raw_n, _ptr(work), work.numel(),
+                                                          _ptr(status), _stream()))
+            else:
+                check(self.L.hufb200_decompress_blocks_dev(self.k, self.block_size, _ptr(comp), _ptr(offsets),
+                                                           _ptr(sizes), nb, _ptr(out), raw_n, _ptr(status), _stream()))
         return out
+
+    def split_work_bytes(self, raw_n):
+        with torch.cuda.device(self.device):
+            return self.L.hufb200_decompress_split_work_bytes(self.k, self.block_size, self.n_blocks(raw_n), raw_n)

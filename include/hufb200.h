@@ -133,6 +133,21 @@ HUFB200_API int hufb200_decompress_blocks_dev(int k, size_t block_size, const ui
                                   const uint64_t* d_offsets, const uint32_t* d_comp_sizes,
                                   size_t n_blocks, uint8_t* d_raw, size_t raw_n,
                                   uint32_t* d_status, void* stream);
+/* Split decode: the same result as hufb200_decompress_blocks_dev for inputs whose n_blocks * k
+ * streams are too few to fill the device (one large buffer: k lanes).  DecompressMulti<K>
+ * (codec/huffman.cpp:892-955) reads each stream from its first bit; here every stream is cut into
+ * items of a few thousand bits, each decoded by its own lane from a guessed start -- prefix codes
+ * fall into step after a few codes -- until the starts are consistent (what never falls into step
+ * is decoded serially behind the last good item), then written out with one lane per item.
+ * d_work: hufb200_decompress_split_work_bytes() bytes, 256-byte aligned, contents irrelevant.
+ * hufb200_decompress_prefers_split: the library's own choice between the two (the host-pointer
+ * calls apply it themselves). */
+HUFB200_API size_t hufb200_decompress_split_work_bytes(int k, size_t block_size, size_t n_blocks, size_t raw_n);
+HUFB200_API int hufb200_decompress_prefers_split(int k, size_t n_blocks, size_t raw_n);
+HUFB200_API int hufb200_decompress_split_dev(int k, size_t block_size, const uint8_t* d_comp,
+                                 const uint64_t* d_offsets, const uint32_t* d_comp_sizes,
+                                 size_t n_blocks, uint8_t* d_raw, size_t raw_n, void* d_work,
+                                 size_t work_bytes, uint32_t* d_status, void* stream);
 /* Gathers the slots into one packed byte string: block b is copied to d_packed + d_offsets[b],
  * where d_offsets = exclusive prefix sum of d_comp_sizes (computed here, on the device). */
 HUFB200_API int hufb200_pack_blocks_dev(const uint8_t* d_slots, size_t slot_stride,
