@@ -508,7 +508,13 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
                                                                const uint8_t* sp, uint32_t sz, bool* overflow,
                                                                const uint8_t* lim, uint32_t bitpos0 = 0) {
   const int lane = lane_id();
-  const bool aligned = (((uintptr_t)sp) & 15) == 0;
+  // A slice that does not start on a 16-byte boundary (K does not divide the block nicely, e.g.
+  // K = 48) is read from the boundary in front of it: every load is an aligned 128-bit load, and
+  // the `mis` symbols in front of the slice -- all in lane 0 of the first group -- contribute no
+  // bits.  (The input base and the block size are multiples of 16, so that boundary is never in
+  // front of the buffer.)  mis is re-derived from sp where it is needed instead of being kept in
+  // a register across the loop.
+  constexpr bool aligned = true;
   uint32_t bitpos = kPiece ? bitpos0 : 0u;  // where the first code goes (long streams are staged piecewise, see below); the end position is returned
   bool over = false;
   uint32_t flag = 0;  // OR of the entry sums: bits 12..16 set <=> some symbol had no code
@@ -517,13 +523,15 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   // A trip in two halves, so that the registers holding its 16 symbols are free -- and the load
   // of the trip after next can be issued into them -- before the long half starts.
   // kFull: every lane has 16 symbols; else `valid` of them (symbols past the slice's end contribute no bits)
-  auto gather = [&](const uint4& v, auto full_tag, uint32_t valid, uint32_t (&E)[16]) {
+  // kFull: every lane has 16 symbols; else the symbols [first, valid) of the 16 (symbols outside the slice contribute no bits)
+  auto gather = [&](const uint4& v, auto full_tag, uint32_t valid, uint32_t (&E)[16], uint32_t first = 0) {
     constexpr bool kFull = decltype(full_tag)::value;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) E[4 * j + i] = (kFull || (uint32_t)(4 * j + i) < valid) ? entry2(w[j], i) : 0u;
+      for (int i = 0; i < 4; ++i)
+        E[4 * j + i] = (kFull || ((uint32_t)(4 * j + i) < valid && (uint32_t)(4 * j + i) >= first)) ? entry2(w[j], i) : 0u;
   };
   auto finish = [&](const uint32_t (&E)[16]) {
     uint32_t Q[4], Qlo[4], S[4];
@@ -570,14 +578,14 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
   // next are requested as soon as a trip's lookups are issued (two trips per iteration, so the
   // two register sets just swap roles).  The loop exists twice: slices that start on a 16-byte
   // boundary (all shapes where K divides the block nicely) take plain 128-bit loads.
-  uint32_t groups = sz >> 9;  // full groups still to do
+  uint32_t groups = (sz + (uint32_t)((uintptr_t)sp & 15u)) >> 9;  // full groups still to do, counted from the boundary
   // keep the trip count and the shared-memory bases in registers: under the kernel's register
   // cap the compiler would otherwise re-derive them from the slice geometry and %warpid every trip
   asm volatile("" : "+r"(groups), "+r"(sb), "+r"(enc_addr));
-  const uint32_t off = lane * 16 + ((sz >> 9) << 9);  // this lane's symbols of the partial last group
-  auto full_groups = [&](auto aligned_tag) {
-    constexpr bool kAligned = decltype(aligned_tag)::value;
-    const uint8_t* p = sp + lane * 16;  // this lane's 16 symbols of the next group
+  {
+    constexpr bool kAligned = true;
+    const uint32_t mis = (uint32_t)((uintptr_t)sp & 15u);
+    const uint8_t* p = sp - mis + lane * 16;  // this lane's 16 symbols of the next group
     auto load = [&](const uint8_t* q) {
       return kAligned ? *reinterpret_cast<const uint4*>(q) : load16(q, 0, 16, false, lim);
     };
@@ -585,6 +593,14 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
     if (groups) va = load(p);
     if (groups >= 2) vb = load(p + 512);
     uint32_t E[16];
+    if (mis != 0 && groups) {  // the first group of a slice that starts off a boundary: lane 0 leaves out what is not ours
+      gather(va, std::false_type{}, 16, E, lane == 0 ? mis : 0u);
+      va = vb;
+      if (groups > 2) vb = load(p + 1024);
+      finish(E);
+      p += 512;
+      groups -= 1;
+    }
     while (groups >= 2) {
       gather(va, std::true_type{}, 16, E);
       if (groups > 2) va = load(p + 1024);
@@ -599,15 +615,18 @@ __device__ inline unsigned long long encode_stream_staged_warp(uint32_t enc_addr
       gather(va, std::true_type{}, 16, E);
       finish(E);
     }
-  };
-  if (aligned) full_groups(std::true_type{});
-  else full_groups(std::false_type{});
-  // the slice's last, partial group
-  if (sz & 511u) {
-    const uint32_t valid = off < sz ? (sz - off < 16 ? sz - off : 16) : 0;
-    uint32_t E[16];
-    gather(load16(sp, off, valid, aligned, lim), std::false_type{}, valid, E);
-    finish(E);
+  }
+  // the slice's last, partial group (also its first if the slice is that short)
+  {
+    const uint32_t mis = (uint32_t)((uintptr_t)sp & 15u);
+    const uint32_t szb = sz + mis;  // counted from the boundary
+    if (szb & 511u) {
+      const uint32_t off = lane * 16 + ((szb >> 9) << 9);  // this lane's symbols of the group
+      const uint32_t valid = off < szb ? (szb - off < 16 ? szb - off : 16) : 0;
+      uint32_t E[16];
+      gather(load16(sp - mis, off, valid, aligned, lim), std::false_type{}, valid, E, (szb >> 9) == 0 && lane == 0 ? mis : 0u);
+      finish(E);
+    }
   }
   __syncwarp();
   *overflow = over;
