@@ -78,11 +78,41 @@ struct DevBuf {
   ~DevBuf() { release(); }
 };
 
+// Grow-only pinned host buffer (staging of the small single-buffer calls).
+struct PinBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (p && n <= cap) return cudaSuccess;
+    release();
+    size_t want = n < (256u << 10) ? (256u << 10) : n;
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return e;
+    }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  ~PinBuf() { release(); }
+};
+// Single-buffer calls of up to this many bytes (either side) go through pinned staging: a copy
+// from or to pageable memory is staged by the driver and blocks the calling thread per copy; with
+// pinned staging a call is one memcpy in, asynchronous copies and kernels, ONE synchronisation and
+// one memcpy out.  (BASELINE config 1 is 100 KiB per call.)
+constexpr size_t kSmallCall = (size_t)2 << 20;
+
 // Per-thread state of the single-buffer host calls: device buffers and one non-blocking stream
 // (never the legacy default stream, which would serialise against everything else the host
 // application runs on the device).
 struct Workspace {
   DevBuf in, out, sizes, offsets, misc, table;
+  PinBuf pin_in, pin_out;
   cudaStream_t st = nullptr;
   int dev = -1;
   cudaError_t ready() {
@@ -105,6 +135,7 @@ struct Workspace {
   }
   void release() {
     in.release(); out.release(); sizes.release(); offsets.release(); misc.release(); table.release();
+    pin_in.release(); pin_out.release();
     if (st) cudaStreamDestroy(st);
     st = nullptr;
     dev = -1;
@@ -214,6 +245,16 @@ bool prefer_split(int k, size_t n_blocks, size_t raw_n) {
   return streams <= 16384 && raw_n / streams >= 4096;
 }
 
+// (HUFB200_SPLIT=0 also switches the one-CTA form off; HUFB200_SPLIT_SMALL=0 only that)
+bool split_small_allowed() {
+  static const bool on = [] {
+    const char* a = getenv("HUFB200_SPLIT");
+    const char* b = getenv("HUFB200_SPLIT_SMALL");
+    return !(a && atoi(a) == 0) && !(b && atoi(b) == 0);
+  }();
+  return on;
+}
+
 int decode_bpc(int k) {
   static const int forced = [] {  // tuning aid: HUFB200_DEC_LANES overrides the lanes per decode CTA
     const char* e = getenv("HUFB200_DEC_LANES");
@@ -257,9 +298,12 @@ int do_compress_dev(int k, size_t block_size, const uint8_t* d_raw, size_t n, ui
 }
 
 // compress one host buffer as `n_blocks` blocks into the workspace; sizes come back in `sizes`
+// staged (one block only): the input goes through ws.pin_in, and size, status and the block's slot
+// up to its bound come back through ws.pin_out ([0] size, [4] status, [64..] bytes) under the one
+// synchronisation -- the caller copies what it needs out of ws.pin_out
 int compress_host(int k, size_t block_size, const uint8_t* raw, size_t n, uint32_t n_blocks,
                   const void* d_table, int check_presence, std::vector<uint32_t>* sizes,
-                  size_t* slot_stride_out) {
+                  size_t* slot_stride_out, bool staged = false) {
   Workspace& ws = g_ws;
   CU(ws.ready());
   const size_t stride = hufb200_slot_stride(block_size, k);
@@ -267,6 +311,13 @@ int compress_host(int k, size_t block_size, const uint8_t* raw, size_t n, uint32
   CU(ws.out.reserve(stride * n_blocks));
   CU(ws.sizes.reserve(sizeof(uint32_t) * (n_blocks + 1)));
   CU(ws.misc.reserve(256));
+  const size_t bound = hufb200_compress_bound(n, k);
+  if (staged) {
+    CU(ws.pin_in.reserve(n + 64));
+    CU(ws.pin_out.reserve(bound + 128));
+    if (n) memcpy(ws.pin_in.p, raw, n);
+    raw = ws.pin_in.p;
+  }
   if (n) CU(cudaMemcpyAsync(ws.in.p, raw, n, cudaMemcpyHostToDevice, ws.st));
   CU(cudaMemsetAsync(ws.misc.p, 0, 4, ws.st));
   int rc = do_compress_dev(k, block_size, ws.in.as<uint8_t>(), n, n_blocks, ws.out.as<uint8_t>(), stride,
@@ -274,9 +325,18 @@ int compress_host(int k, size_t block_size, const uint8_t* raw, size_t n, uint32
   if (rc) return rc;
   sizes->resize(n_blocks);
   uint32_t status = 0;
-  CU(cudaMemcpyAsync(sizes->data(), ws.sizes.p, sizeof(uint32_t) * n_blocks, cudaMemcpyDeviceToHost, ws.st));
-  CU(cudaMemcpyAsync(&status, ws.misc.p, 4, cudaMemcpyDeviceToHost, ws.st));
-  CU(cudaStreamSynchronize(ws.st));
+  if (staged) {
+    CU(cudaMemcpyAsync(ws.pin_out.p, ws.sizes.p, 4, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaMemcpyAsync(ws.pin_out.p + 4, ws.misc.p, 4, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaMemcpyAsync(ws.pin_out.p + 64, ws.out.p, bound, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaStreamSynchronize(ws.st));
+    memcpy(sizes->data(), ws.pin_out.p, 4);
+    memcpy(&status, ws.pin_out.p + 4, 4);
+  } else {
+    CU(cudaMemcpyAsync(sizes->data(), ws.sizes.p, sizeof(uint32_t) * n_blocks, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaMemcpyAsync(&status, ws.misc.p, 4, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaStreamSynchronize(ws.st));
+  }
   if (status) return fail(HUFB200_E_CORRUPT, "a symbol of the input has no code in the supplied table");
   *slot_stride_out = stride;
   return HUFB200_OK;
@@ -293,7 +353,7 @@ int compress_host(int k, size_t block_size, const uint8_t* raw, size_t n, uint32
 inline bool single_goes_wide(size_t n, int k) { return n >= HUF_SINGLE_MULTI_MIN || (k <= 8 && n >= (64u << 10)); }
 
 // compresses one host buffer into ws.out; *size = compressed size
-int compress_single_host(int k, const uint8_t* raw, size_t n, const void* d_table, uint32_t* size) {
+int compress_single_host(int k, const uint8_t* raw, size_t n, const void* d_table, uint32_t* size, bool staged = false) {
   Workspace& ws = g_ws;
   int sms = 0;
   int rc = sm_count(&sms);
@@ -310,14 +370,27 @@ int compress_single_host(int k, const uint8_t* raw, size_t n, const void* d_tabl
   void* d_plan = m + hist_b;
   void* d_tab = m + hist_b + plan_b;
   uint32_t* d_pieces = reinterpret_cast<uint32_t*>(m + hist_b + plan_b + tab_b);
+  if (staged) {  // see compress_host
+    CU(ws.pin_in.reserve(n + 64));
+    CU(ws.pin_out.reserve(bound + 128));
+    memcpy(ws.pin_in.p, raw, n);
+    raw = ws.pin_in.p;
+  }
   CU(cudaMemcpyAsync(ws.in.p, raw, n, cudaMemcpyHostToDevice, ws.st));
   CU(cudaMemsetAsync(ws.out.p, 0, bound, ws.st));  // pieces OR their bits into it
   CU(launch_compress_single(ws.in.as<uint8_t>(), (uint32_t)n, k, d_table, d_hist, d_tab, d_plan, d_pieces,
                             ws.out.as<uint8_t>(), sms, ws.st));
   g_launches.fetch_add(4, std::memory_order_relaxed);
   uint32_t head[4] = {0, 0, 0, 0};  // total_size, hdr_total, bad
-  CU(cudaMemcpyAsync(head, d_plan, sizeof(head), cudaMemcpyDeviceToHost, ws.st));
-  CU(cudaStreamSynchronize(ws.st));
+  if (staged) {
+    CU(cudaMemcpyAsync(ws.pin_out.p, d_plan, sizeof(head), cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaMemcpyAsync(ws.pin_out.p + 64, ws.out.p, bound - 16, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaStreamSynchronize(ws.st));
+    memcpy(head, ws.pin_out.p, sizeof(head));
+  } else {
+    CU(cudaMemcpyAsync(head, d_plan, sizeof(head), cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaStreamSynchronize(ws.st));
+  }
   if (head[2]) return fail(HUFB200_E_CORRUPT, "a symbol of the input has no code in the supplied table");
   *size = head[0];
   return HUFB200_OK;
@@ -496,15 +569,21 @@ int hufb200_compress(int k, const uint8_t* raw, size_t n, uint8_t* out, size_t c
   std::vector<uint32_t> sizes(1);
   size_t stride = 0;
   int rc;
+  const bool staged = n <= kSmallCall;  // small calls: pinned staging, one synchronisation
   if (single_goes_wide(n, k)) {
     CU(g_ws.ready());
-    rc = compress_single_host(k, raw, n, nullptr, &sizes[0]);
+    rc = compress_single_host(k, raw, n, nullptr, &sizes[0], staged);
   } else {
-    rc = compress_host(k, n ? n : 1, raw, n, 1, nullptr, 0, &sizes, &stride);
+    rc = compress_host(k, n ? n : 1, raw, n, 1, nullptr, 0, &sizes, &stride, staged);
   }
   if (rc) return rc;
   *out_len = sizes[0];
   if (sizes[0] > cap) return fail(HUFB200_E_NOSPACE, "need %u bytes, have %zu", sizes[0], cap);
+  if (staged) {
+    if (sizes[0] > hufb200_compress_bound(n, k)) return fail(HUFB200_E_CUDA, "compressed size beyond its bound");
+    memcpy(out, g_ws.pin_out.p + 64, sizes[0]);
+    return HUFB200_OK;
+  }
   CU(cudaMemcpyAsync(out, g_ws.out.p, sizes[0], cudaMemcpyDeviceToHost, g_ws.st));
   CU(cudaStreamSynchronize(g_ws.st));
   return HUFB200_OK;
@@ -563,15 +642,31 @@ int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_
   CU(ws.in.reserve(n + 32));
   CU(ws.out.reserve(raw_size + 16));
   CU(ws.misc.reserve(256));
-  CU(cudaMemcpyAsync(ws.in.p, comp, n, cudaMemcpyHostToDevice, ws.st));
-  struct {
+  struct Meta {
     unsigned long long off;
     uint32_t size;
     uint32_t status;
   } meta = {0ull, (uint32_t)n, 0u};
-  CU(cudaMemcpyAsync(ws.misc.p, &meta, sizeof(meta), cudaMemcpyHostToDevice, ws.st));
+  const bool small = n <= kSmallCall && raw_size <= kSmallCall;
+  if (small) {  // pinned staging: [meta | compressed bytes] in, [status | raw bytes] out
+    CU(ws.pin_in.reserve(n + 64));
+    CU(ws.pin_out.reserve(raw_size + 64));
+    memcpy(ws.pin_in.p, &meta, sizeof(meta));
+    memcpy(ws.pin_in.p + 32, comp, n);
+    CU(cudaMemcpyAsync(ws.in.p, ws.pin_in.p + 32, n, cudaMemcpyHostToDevice, ws.st));
+    CU(cudaMemcpyAsync(ws.misc.p, ws.pin_in.p, sizeof(meta), cudaMemcpyHostToDevice, ws.st));
+  } else {
+    CU(cudaMemcpyAsync(ws.in.p, comp, n, cudaMemcpyHostToDevice, ws.st));
+    CU(cudaMemcpyAsync(ws.misc.p, &meta, sizeof(meta), cudaMemcpyHostToDevice, ws.st));
+  }
   uint8_t* m = ws.misc.as<uint8_t>();
-  if (prefer_split(k, 1, raw_size)) {  // K streams cannot fill the device: cut them into items
+  if (raw_size / (size_t)k >= 1024 && split_small_fits(n, k) && split_small_allowed()) {
+    // a small buffer: the whole split decode in one CTA, one launch
+    CU(launch_decompress_split_small(ws.in.as<uint8_t>(), reinterpret_cast<uint32_t*>(m + 8), n, k,
+                                     ws.out.as<uint8_t>(), (uint32_t)raw_size, reinterpret_cast<uint32_t*>(m + 12),
+                                     ws.st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else if (prefer_split(k, 1, raw_size)) {  // K streams cannot fill the device: cut them into items
     int sms = 0;
     rc = sm_count(&sms);
     if (rc) return rc;
@@ -590,9 +685,17 @@ int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_
     g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   uint32_t status = 0;
-  CU(cudaMemcpyAsync(&status, m + 12, 4, cudaMemcpyDeviceToHost, ws.st));
-  if (raw_size) CU(cudaMemcpyAsync(out, ws.out.p, raw_size, cudaMemcpyDeviceToHost, ws.st));
-  CU(cudaStreamSynchronize(ws.st));
+  if (small) {
+    CU(cudaMemcpyAsync(ws.pin_out.p, m + 12, 4, cudaMemcpyDeviceToHost, ws.st));
+    if (raw_size) CU(cudaMemcpyAsync(ws.pin_out.p + 32, ws.out.p, raw_size, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaStreamSynchronize(ws.st));
+    memcpy(&status, ws.pin_out.p, 4);
+    if (!status && raw_size) memcpy(out, ws.pin_out.p + 32, raw_size);
+  } else {
+    CU(cudaMemcpyAsync(&status, m + 12, 4, cudaMemcpyDeviceToHost, ws.st));
+    if (raw_size) CU(cudaMemcpyAsync(out, ws.out.p, raw_size, cudaMemcpyDeviceToHost, ws.st));
+    CU(cudaStreamSynchronize(ws.st));
+  }
   if (status) return fail(HUFB200_E_CORRUPT, "malformed compressed buffer");
   return HUFB200_OK;
 }
@@ -849,6 +952,7 @@ int hufb200_decompress_split_dev(int k, size_t block_size, const uint8_t* d_comp
   if (hufb200_blocks_count(raw_n, block_size) != n_blocks)
     return fail(HUFB200_E_INVALID, "n_blocks does not match raw_n / block_size");
   if (n_blocks && (!d_comp || !d_offsets || !d_comp_sizes || !d_raw || !d_work)) return fail(HUFB200_E_INVALID, "null pointer");
+  if ((n_blocks * (size_t)k) >> 31) return fail(HUFB200_E_INVALID, "too many streams for the split decode");
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;

@@ -1736,7 +1736,7 @@ struct SplitReader {
 // returns that boundary and adds the number of codes passed to cnt.  T: the block's decode table
 // (build_dtable<BITS, 3, true>), c_l: its level bases.
 template <int BITS>
-__device__ __forceinline__ uint32_t split_walk(const uint32_t* T, const DecBlockInfo& bi, const int (&c_l)[kMaxCodeLen - BITS + 1],
+__device__ __forceinline__ uint32_t split_walk(const uint32_t* T, const uint8_t* L1, const int (&c_l)[kMaxCodeLen - BITS + 1],
                                                const SplitReader& rd, uint32_t pad_bits, uint32_t pos, uint32_t limit,
                                                uint32_t& cnt) {
   if (pos >= limit) return pos;
@@ -1762,12 +1762,18 @@ __device__ __forceinline__ uint32_t split_walk(const uint32_t* T, const DecBlock
       lo = rd.word(wi + 1);
     }
   }
-  // near the end: one code at a time, its length by the canonical ranges (code_end is the
-  // left-aligned end of each length's range; the code is complete, so the walk ends by 12)
+  // near the end: one code at a time.  Its length: what build_dtable left in L1 for the window's
+  // first BITS bits (the first code's own length), or -- 15 there: a longer code -- the length in
+  // that code's own entry
   while (P < Plimit) {
-    const uint32_t v = __funnelshift_l(lo, hi, P) >> (32 - kMaxCodeLen);
-    uint32_t l = 1;
-    while (l < (uint32_t)kMaxCodeLen && v >= bi.code_end[l]) ++l;
+    const uint32_t win = __funnelshift_l(lo, hi, P);
+    uint32_t l = L1[win >> (32 - BITS)];
+    if (l > (uint32_t)BITS) {
+      int idx = (int)(win >> (32 - BITS));
+#pragma unroll
+      for (int q = BITS + 1; q <= kMaxCodeLen; ++q) idx = max(idx, (int)(win >> (32 - q)) + c_l[q - BITS - 1]);
+      l = (T[idx] >> 24) & 15u;
+    }
     P += l;
     ++cnt;
     if ((P >> 5) != wi) {
@@ -1866,13 +1872,245 @@ k_split_sync(const uint8_t* __restrict__ comp, const unsigned long long* __restr
       const uint32_t first_bit = j * sa.sub_bits;
       const uint32_t warm = sa.sub_bits / 2 < 512u ? sa.sub_bits / 2 : 512u;
       uint32_t dummy = 0;
-      start = split_walk<BITS>(T, bi, c_l, rd, pad_bits, first_bit - warm, first_bit, dummy);
+      start = split_walk<BITS>(T, L1, c_l, rd, pad_bits, first_bit - warm, first_bit, dummy);
     }
-    pos = split_walk<BITS>(T, bi, c_l, rd, pad_bits, start, limit, cnt);
+    pos = split_walk<BITS>(T, L1, c_l, rd, pad_bits, start, limit, cnt);
   }
   sa.start[gi] = start;
   sa.cnt[gi] = cnt;
   exit_cur[gi] = pos;
+}
+
+// ---- the whole split decode of ONE small buffer in ONE CTA (one launch instead of seven): the
+// reference's own benchmark unit is a 100 KiB buffer per call (codec/huffman_benchmark.cpp:61-81),
+// where launches and table builds are most of a call.  One item per thread; the item arrays live
+// in registers and shared memory; the phases of k_split_plan / k_split_sync / k_split_scan and the
+// write pass are separated by __syncthreads.  sub_bits is chosen by the host so that the items
+// fit the CTA (8 * comp_size / sub_bits + K <= kSmallItems).
+constexpr int kSmallItems = 1024;
+// Decodes `cnt` symbols from stream bit `pos` on and stores them at out (byte stores up to a
+// 4-byte boundary, then words).
+template <int BITS>
+__device__ __forceinline__ void split_write_lane(const uint32_t* T, const int (&c_l)[kMaxCodeLen - BITS + 1],
+                                                 const SplitReader& rd, uint32_t pad_bits, uint32_t pos, uint32_t cnt,
+                                                 uint8_t* out) {
+  if (cnt == 0) return;
+  uint32_t P = pad_bits + pos;
+  uint32_t wi = P >> 5;
+  uint32_t hi = rd.word(wi), lo = rd.word(wi + 1);
+  unsigned long long buf = 0;  // decoded symbols not stored yet, first symbol in the low byte
+  uint32_t fill = 0;
+  while (cnt) {
+    const uint32_t win = __funnelshift_l(lo, hi, P);
+    int idx = (int)(win >> (32 - BITS));
+#pragma unroll
+    for (int l = BITS + 1; l <= kMaxCodeLen; ++l) idx = max(idx, (int)(win >> (32 - l)) + c_l[l - BITS - 1]);
+    const uint32_t e = T[idx];
+    P += (e >> 24) & 15u;
+    uint32_t n = e >> 30;  // 1..3 symbols (the last entry of an item may hold more than are left)
+    if (n > cnt) n = cnt;
+    cnt -= n;
+    buf |= (unsigned long long)(e & (0xffffffu >> (8u * (3u - n)))) << (8u * fill);
+    fill += n;
+    if ((P >> 5) != wi) {
+      ++wi;
+      hi = lo;
+      lo = rd.word(wi + 1);
+    }
+    while (fill >= 4u || (fill && ((uintptr_t)out & 3u))) {
+      if (((uintptr_t)out & 3u) == 0 && fill >= 4u) {
+        *reinterpret_cast<uint32_t*>(out) = (uint32_t)buf;
+        out += 4;
+        buf >>= 32;
+        fill -= 4;
+      } else {
+        *out++ = (uint8_t)buf;
+        buf >>= 8;
+        fill -= 1;
+      }
+    }
+  }
+  for (; fill; --fill) {
+    *out++ = (uint8_t)buf;
+    buf >>= 8;
+  }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kSmallItems)
+k_split_small(const uint8_t* __restrict__ comp, const uint32_t* __restrict__ comp_size_p, int K, uint8_t* __restrict__ raw,
+              uint32_t raw_n, uint32_t sub_bits, uint32_t* __restrict__ status) {
+  constexpr int kEntries = dec_entries(BITS);
+  __shared__ uint32_t T[kEntries];
+  __shared__ __align__(16) uint8_t L1[kEntries];
+  __shared__ DecBlockInfo bi;
+  __shared__ uint32_t sf[kMaxK + 1], sn[kMaxK], seoff[kMaxK], sbits[kMaxK], sjbad[kMaxK], sbase[kMaxK], scounted[kMaxK];
+  __shared__ uint32_t exit_a[kSmallItems], exit_b[kSmallItems];
+  __shared__ uint32_t warp_tot[kSmallItems / 32];
+  __shared__ uint32_t bad_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint8_t* blk = comp;
+  if (tid == 0) {
+    bad_s = 0;
+    parse_header(blk, *comp_size_p, K, raw_n, &bi, false);
+  }
+  __syncthreads();
+  if (!bi.ok) {
+    if (tid == 0 && status) atomicOr(status, 1u);
+    return;
+  }
+  if (bi.raw_size == 0) return;
+  copy_header_syms(blk, &bi, tid, kSmallItems);
+  // ---- plan (k_split_plan): thread s takes stream s
+  if (tid < K) {
+    const uint32_t payload = bi.comp_size - bi.payload_off;
+    auto end_of = [&](int s) -> uint32_t {  // :901
+      if (s == K - 1) return payload;
+      const uint8_t* p = blk + bi.ends_off + 4 * s;
+      return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    };
+    const uint32_t e_off = end_of(tid), e_prev = tid ? end_of(tid - 1) : 0u;
+    uint32_t n = 0, bits = 0;
+    if (e_off > payload || e_prev > e_off || e_off - e_prev < (uint32_t)kSlop) {
+      bad_s = 1;
+    } else {
+      bits = 8u * (e_off - e_prev - (uint32_t)kSlop);
+      n = (bits + sub_bits - 1) / sub_bits;
+      if (n == 0) n = 1;
+    }
+    sn[tid] = n;
+    seoff[tid] = e_off;
+    sbits[tid] = bits;
+    sjbad[tid] = n;
+  }
+  __syncthreads();
+  build_dtable<BITS, 3, true>(&bi, bi.syms, T, L1, tid, kSmallItems);  // (ends with a barrier)
+  if (tid == 0) {
+    uint32_t tot = 0;
+    for (int s = 0; s < K; ++s) {
+      sf[s] = tot;
+      tot += sn[s];
+    }
+    sf[K] = tot;
+    if (tot > (uint32_t)kSmallItems) bad_s = 1;  // (the host sized sub_bits for the buffer: a lying header)
+  }
+  __syncthreads();
+  if (bad_s) {
+    if (tid == 0 && status) atomicOr(status, 1u);
+    return;
+  }
+  // ---- this thread's item
+  int s = -1;
+  uint32_t j = 0;
+  for (int q = 0; q < K; ++q)
+    if ((uint32_t)tid >= sf[q] && (uint32_t)tid - sf[q] < sn[q]) {
+      s = q;
+      j = (uint32_t)tid - sf[q];
+    }
+  const bool active = s >= 0;
+  const bool lone = bi.code_end[0] != 0;  // the empty code: no bits, one item per stream yields its whole slice
+  SplitReader rd{};
+  uint32_t pad_bits = 0, limit = 0;
+  int c_l[kMaxCodeLen - BITS + 1];
+  {
+    uint32_t base = bi.code_end[BITS] >> (kMaxCodeLen - BITS);
+#pragma unroll
+    for (int l = BITS + 1; l <= kMaxCodeLen; ++l) {
+      const uint32_t first = bi.code_end[l - 1] >> (kMaxCodeLen - l);
+      c_l[l - BITS - 1] = (int)base - (int)first;
+      base += (bi.code_end[l] - bi.code_end[l - 1]) >> (kMaxCodeLen - l);
+    }
+  }
+  if (active) {
+    const uintptr_t end_addr = (uintptr_t)(blk + bi.payload_off) + seoff[s];
+    rd.wend = (end_addr + 3) & ~(uintptr_t)3;
+    rd.lo_lim = (uintptr_t)blk & ~(uintptr_t)3;
+    pad_bits = 8u * (uint32_t)(rd.wend - end_addr);
+    limit = (j + 1) * sub_bits;
+    if (limit > sbits[s] || j + 1 == sn[s]) limit = sbits[s];
+  }
+  // ---- pass 0 (k_split_sync): warm-up, then decode to the exit and count
+  uint32_t start = 0, cnt = 0, ex = 0;
+  if (active && !lone) {
+    if (j != 0) {
+      const uint32_t first_bit = j * sub_bits;
+      const uint32_t warm = sub_bits / 2 < 512u ? sub_bits / 2 : 512u;
+      uint32_t dummy = 0;
+      start = split_walk<BITS>(T, L1, c_l, rd, pad_bits, first_bit - warm, first_bit, dummy);
+    }
+    ex = split_walk<BITS>(T, L1, c_l, rd, pad_bits, start, limit, cnt);
+  }
+  exit_a[tid] = ex;
+  __syncthreads();
+  // ---- two repair passes
+  uint32_t* e_prev_buf = exit_a;
+  uint32_t* e_cur_buf = exit_b;
+#pragma unroll 1
+  for (int pass = 1; pass < 3; ++pass) {
+    if (active && !lone && j != 0) {
+      const uint32_t want = e_prev_buf[tid - 1];
+      if (want != start) {
+        start = want;
+        cnt = 0;
+        ex = split_walk<BITS>(T, L1, c_l, rd, pad_bits, start, limit, cnt);
+      }
+    }
+    e_cur_buf[tid] = ex;
+    __syncthreads();
+    uint32_t* t = e_prev_buf;
+    e_prev_buf = e_cur_buf;
+    e_cur_buf = t;
+  }
+  const uint32_t* exf = e_prev_buf;  // the exits of the last pass
+  // ---- scan (k_split_scan): consistent prefix of every stream, offsets, the serial tail, the totals
+  if (active && j != 0 && start != exf[tid - 1]) atomicMin(&sjbad[s], j);
+  __syncthreads();
+  const uint32_t jbad = active ? sjbad[s] : 0u;
+  const uint32_t c = (active && j < jbad) ? cnt : 0u;
+  const uint32_t incl_w = warp_incl_scan(c);
+  if (lane == 31) warp_tot[warp] = incl_w;
+  __syncthreads();
+  uint32_t before = 0;
+  for (int w = 0; w < warp; ++w) before += warp_tot[w];
+  const uint32_t incl = before + incl_w;
+  if (active && j == 0) sbase[s] = incl - c;
+  if (active && j + 1 == sn[s]) scounted[s] = incl;  // minus sbase[s] below
+  __syncthreads();
+  uint32_t st = 0, sz = 0, off = 0;
+  if (active) {
+    slice_geom(bi.raw_size, K, s, st, sz);
+    off = incl - c - sbase[s];
+    const uint32_t counted = scounted[s] - sbase[s];
+    const uint32_t n = sn[s];
+    bool bad = false;
+    if (lone) {
+      cnt = j == 0 ? sz : 0u;
+      off = 0;
+    } else if (jbad < n) {  // what lies behind the last consistent item: one serial item
+      if (counted > sz) bad = true;
+      if (j > jbad) cnt = 0;
+      if (j == jbad) {
+        start = exf[tid - 1];
+        cnt = sz - counted;
+        off = counted;
+      }
+    } else {  // only the last item can have counted too much (the < 8 pad bits behind the stream)
+      if (counted < sz || counted - sz > 7u) bad = true;
+      else if (j + 1 == n) {
+        if (counted - sz > cnt) bad = true;
+        else cnt -= counted - sz;
+      }
+    }
+    if (bad) {
+      cnt = 0;
+      atomicOr(&bad_s, 1u);
+    }
+    if (off > sz || cnt > sz - off) cnt = 0;  // (never outside the slice, whatever the input)
+  }
+  // ---- write pass
+  if (active) split_write_lane<BITS>(T, c_l, rd, pad_bits, start, cnt, raw + st + off);
+  __syncthreads();
+  if (tid == 0 && bad_s && status) atomicOr(status, 1u);
 }
 
 // One CTA per stream.  final_pass: the pass whose exits are current.
@@ -2446,6 +2684,20 @@ size_t decompress_split_work_bytes(uint32_t n_blocks, int K, uint32_t block_size
   size_t total = 0;
   split_layout(nullptr, n_blocks, K, block_size, sub_bits, &total);
   return total;
+}
+
+// One small buffer (compressed size known to the host): the whole split decode as one CTA.
+// (one SM: 45 us per 100 KiB of raw bytes; the seven launches of the spread form take about 110 us
+// for anything up to a few MiB -- profiles/r2_split_decode.md)
+bool split_small_fits(uint64_t comp_bytes, int K) { return comp_bytes <= (128u << 10) && K < kSmallItems / 2; }
+cudaError_t launch_decompress_split_small(const uint8_t* d_comp, const uint32_t* d_size, uint64_t comp_bytes, int K,
+                                          uint8_t* d_raw, uint32_t raw_n, uint32_t* d_status, cudaStream_t st) {
+  // items of 8 * comp_bytes / (kSmallItems - K) bits, rounded up to a multiple of 32, at least 256
+  uint64_t sub = (8u * comp_bytes + (uint64_t)(kSmallItems - K) - 1) / (uint64_t)(kSmallItems - K);
+  sub = (sub + 31) & ~(uint64_t)31;
+  if (sub < 256) sub = 256;
+  k_split_small<kSplitBits><<<1, kSmallItems, 0, st>>>(d_comp, d_size, K, d_raw, raw_n, (uint32_t)sub, d_status);
+  return cudaGetLastError();
 }
 
 constexpr int kSplitPasses = 3;  // pass 0 and two repairs; what is still out of step decodes serially (k_split_scan)

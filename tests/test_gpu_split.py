@@ -121,13 +121,46 @@ def test_split_decode_of_our_own_slots_at_size(huf):
 def test_single_buffer_calls_take_the_split_path(huf, oracle):
     """hufb200_decompress of one large buffer (K streams only) goes through the split decode."""
     L = huf.load()
-    for k, n in ((32, 8 << 20), (4, (1 << 20) + 3), (1, 300000)):
+    for k, n in ((32, 8 << 20), (4, (1 << 20) + 3), (1, 300000), (48, 3 << 20), (8, 100 << 10), (32, 200000)):
         data = english(n, seed=k)
-        assert L.hufb200_decompress_prefers_split(k, 1, n) == 1
         comp = oracle.compress(k, data)
         before = huf.launch_count()
         assert huf.decompress(k, comp) == data
-        assert huf.launch_count() - before > 1  # plan, scan, passes, write: not the single launch
+        launches = huf.launch_count() - before
+        if len(comp) <= (128 << 10):
+            assert launches == 1  # the whole split decode as one CTA (k_split_small)
+        else:
+            assert launches > 1  # plan, scan, passes, item scan, write: not the single launch
+
+
+@pytest.mark.parametrize("name", ["biased", "english", "seven_bit", "uniform", "two_symbols", "lone_symbol",
+                                  "long_codes", "text"])
+def test_small_single_buffers_one_cta_split(huf, oracle, name):
+    """hufb200_decompress of small buffers (k_split_small up to 128 KiB compressed, the spread form above), every K class, ragged sizes."""
+    for k in (1, 3, 4, 8, 16, 32, 48, 64):
+        for n in (k * 1024, 100 << 10, 33333 + 1024 * k, (1 << 20) + 17):
+            data = _inputs()[name](n)
+            comp = oracle.compress(k, data)
+            assert huf.decompress(k, comp) == data, (name, k, n)
+
+
+def test_small_single_buffer_corruption(huf, oracle):
+    """The one-CTA form on damaged buffers: an error or output of the right length, never a fault."""
+    k = 8
+    data = biased(100 << 10, seed=4)
+    good = bytearray(oracle.compress(k, data))
+    rng = np.random.default_rng(3)
+    for trial in range(80):
+        bad = bytearray(good)
+        for _ in range(int(rng.integers(1, 6))):
+            bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+        bad[0:4] = good[0:4]  # keep raw_size: the caller sizes its buffer from it
+        try:
+            out = huf.decompress(k, bytes(bad))
+            assert len(out) == len(data)
+        except huf.HufError as e:
+            assert e.code == -4  # HUFB200_E_CORRUPT
+    assert huf.decompress(k, bytes(good)) == data
 
 
 def test_split_decode_survives_corrupt_input(huf, oracle):
