@@ -273,7 +273,7 @@ def config1_table(huf, seconds=0.25):
         res["compressed_bytes"] = clen.value
         out["rows"][f"HuffmanCompressorB200<{k}>"] = res
     # one LARGE buffer through the same two calls (pinned host memory): compress spreads pieces of
-    # the K streams over the device; decompress has K serial streams and nothing finer to work on
+    # the K streams over the device; decompress cuts the K streams into items (split decode)
     import torch
     from _cases import biased
     nl = 64 << 20
@@ -290,7 +290,7 @@ def config1_table(huf, seconds=0.25):
         huf.binding.check(L.hufb200_decompress(32, C.c_void_p(compl.data_ptr()), clen.value,
                                                C.c_void_p(backl.data_ptr()), nl, C.byref(olen)))
     tms = {}
-    for name, fn, reps in (("compress", lc, 5), ("decompress", ld, 2)):
+    for name, fn, reps in (("compress", lc, 5), ("decompress", ld, 5)):
         fn()
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -300,7 +300,8 @@ def config1_table(huf, seconds=0.25):
     out["single_buffer_64MiB_K32"] = {"host_memory": "pinned", "compress_ms": tms["compress"] * 1e3,
                                       "compress_GBps": nl / tms["compress"] / GB, "decompress_ms": tms["decompress"] * 1e3,
                                       "decompress_GBps": nl / tms["decompress"] / GB,
-                                      "note": "decompress of one buffer = 32 serial streams on 32 lanes; blocks are the scalable form"}
+                                      "note": "both through the host-pointer calls (PCIe inside); decompress = split decode, "
+                                              "32 streams cut into items of 4 Kbit, one lane per item"}
     del big, compl, backl
     if have_ref():
         r = Ref()

@@ -1743,7 +1743,7 @@ __device__ __forceinline__ uint32_t split_walk(const uint32_t* T, const uint8_t*
   uint32_t P = pad_bits + pos;  // virtual bit position
   const uint32_t Plimit = pad_bits + limit;
   uint32_t wi = P >> 5;
-  uint32_t hi = rd.word(wi), lo = rd.word(wi + 1);
+  uint32_t hi = rd.word(wi), lo = rd.word(wi + 1), nx = rd.word(wi + 2);  // nx: requested one word ahead of its use
   // far from the end: whole table entries (up to three symbols); an entry never spans more than
   // BITS bits and a longer code has an entry of its own, so 3 * 12 bits of margin keep every
   // code that starts in front of the limit counted one by one below
@@ -1759,7 +1759,8 @@ __device__ __forceinline__ uint32_t split_walk(const uint32_t* T, const uint8_t*
     if ((P >> 5) != wi) {
       ++wi;
       hi = lo;
-      lo = rd.word(wi + 1);
+      lo = nx;
+      nx = rd.word(wi + 2);
     }
   }
   // near the end: one code at a time.  Its length: what build_dtable left in L1 for the window's
@@ -1779,7 +1780,8 @@ __device__ __forceinline__ uint32_t split_walk(const uint32_t* T, const uint8_t*
     if ((P >> 5) != wi) {
       ++wi;
       hi = lo;
-      lo = rd.word(wi + 1);
+      lo = nx;
+      nx = rd.word(wi + 2);
     }
   }
   return P - pad_bits;
@@ -1897,7 +1899,7 @@ __device__ __forceinline__ void split_write_lane(const uint32_t* T, const int (&
   if (cnt == 0) return;
   uint32_t P = pad_bits + pos;
   uint32_t wi = P >> 5;
-  uint32_t hi = rd.word(wi), lo = rd.word(wi + 1);
+  uint32_t hi = rd.word(wi), lo = rd.word(wi + 1), nx = rd.word(wi + 2);  // nx: requested one word ahead of its use
   unsigned long long buf = 0;  // decoded symbols not stored yet, first symbol in the low byte
   uint32_t fill = 0;
   while (cnt) {
@@ -1915,7 +1917,8 @@ __device__ __forceinline__ void split_write_lane(const uint32_t* T, const int (&
     if ((P >> 5) != wi) {
       ++wi;
       hi = lo;
-      lo = rd.word(wi + 1);
+      lo = nx;
+      nx = rd.word(wi + 2);
     }
     while (fill >= 4u || (fill && ((uintptr_t)out & 3u))) {
       if (((uintptr_t)out & 3u) == 0 && fill >= 4u) {
