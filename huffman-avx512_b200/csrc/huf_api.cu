@@ -660,7 +660,7 @@ int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_
     CU(cudaMemcpyAsync(ws.misc.p, &meta, sizeof(meta), cudaMemcpyHostToDevice, ws.st));
   }
   uint8_t* m = ws.misc.as<uint8_t>();
-  if (raw_size / (size_t)k >= 1024 && split_small_fits(n, k) && split_small_allowed()) {
+  if (small && raw_size / (size_t)k >= 1024 && split_small_fits(n, k) && split_small_allowed()) {
     // a small buffer: the whole split decode in one CTA, one launch
     CU(launch_decompress_split_small(ws.in.as<uint8_t>(), reinterpret_cast<uint32_t*>(m + 8), n, k,
                                      ws.out.as<uint8_t>(), (uint32_t)raw_size, reinterpret_cast<uint32_t*>(m + 12),
@@ -690,6 +690,26 @@ int hufb200_decompress(int k, const uint8_t* comp, size_t n, uint8_t* out, size_
     if (raw_size) CU(cudaMemcpyAsync(ws.pin_out.p + 32, ws.out.p, raw_size, cudaMemcpyDeviceToHost, ws.st));
     CU(cudaStreamSynchronize(ws.st));
     memcpy(&status, ws.pin_out.p, 4);
+    if (status == kSplitSmallRetry) {
+      // the one-launch form found a CTA with more than 1.5 times its share of the bits (streams of
+      // very unequal length): the spread form has no such limit
+      int sms = 0;
+      rc = sm_count(&sms);
+      if (rc) return rc;
+      const uint32_t sub = split_sub_bits(raw_size, 1, k, sms);
+      CU(ws.offsets.reserve(decompress_split_work_bytes(1, k, (uint32_t)raw_size, sub)));
+      CU(cudaMemsetAsync(m + 12, 0, 4, ws.st));
+      int launches = 0;
+      CU(launch_decompress_split(ws.in.as<uint8_t>(), reinterpret_cast<unsigned long long*>(m),
+                                 reinterpret_cast<uint32_t*>(m + 8), 1, k, ws.out.as<uint8_t>(), raw_size,
+                                 (uint32_t)raw_size, sub, ws.offsets.p, reinterpret_cast<uint32_t*>(m + 12), &launches,
+                                 ws.st));
+      g_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
+      CU(cudaMemcpyAsync(ws.pin_out.p, m + 12, 4, cudaMemcpyDeviceToHost, ws.st));
+      CU(cudaMemcpyAsync(ws.pin_out.p + 32, ws.out.p, raw_size, cudaMemcpyDeviceToHost, ws.st));
+      CU(cudaStreamSynchronize(ws.st));
+      memcpy(&status, ws.pin_out.p, 4);
+    }
     if (!status && raw_size) memcpy(out, ws.pin_out.p + 32, raw_size);
   } else {
     CU(cudaMemcpyAsync(&status, m + 12, 4, cudaMemcpyDeviceToHost, ws.st));

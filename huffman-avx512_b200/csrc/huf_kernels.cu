@@ -1883,13 +1883,17 @@ k_split_sync(const uint8_t* __restrict__ comp, const unsigned long long* __restr
   exit_cur[gi] = pos;
 }
 
-// ---- the whole split decode of ONE small buffer in ONE CTA (one launch instead of seven): the
-// reference's own benchmark unit is a 100 KiB buffer per call (codec/huffman_benchmark.cpp:61-81),
-// where launches and table builds are most of a call.  One item per thread; the item arrays live
-// in registers and shared memory; the phases of k_split_plan / k_split_sync / k_split_scan and the
-// write pass are separated by __syncthreads.  sub_bits is chosen by the host so that the items
-// fit the CTA (8 * comp_size / sub_bits + K <= kSmallItems).
+// ---- the whole split decode of ONE small buffer in ONE launch instead of seven: the reference's
+// own benchmark unit is a 100 KiB buffer per call (codec/huffman_benchmark.cpp:61-81), where
+// launches and table builds are most of a call.  The K streams are dealt out to up to eight CTAs
+// (whole streams: nothing crosses a CTA); one item per thread; the item arrays live in registers
+// and shared memory; the phases of k_split_plan / k_split_sync / k_split_scan and the write pass
+// are separated by __syncthreads.  The host sizes sub_bits for a CTA that gets 1.5 times its share
+// of the bits; a CTA whose streams hold more than kSmallItems items reports kSplitRetry and the
+// host takes the spread form.
 constexpr int kSmallItems = 1024;
+constexpr int kSmallMaxCtas = 8;
+constexpr uint32_t kSplitRetry = 2u;  // status bit: the items did not fit, nothing usable was written
 // Decodes `cnt` symbols from stream bit `pos` on and stores them at out (byte stores up to a
 // 4-byte boundary, then words).
 template <int BITS>
@@ -1988,24 +1992,25 @@ k_split_small(const uint8_t* __restrict__ comp, const uint32_t* __restrict__ com
   }
   __syncthreads();
   build_dtable<BITS, 3, true>(&bi, bi.syms, T, L1, tid, kSmallItems);  // (ends with a barrier)
+  // this CTA's streams
+  const int s_lo = (int)(((long long)blockIdx.x * K) / (int)gridDim.x), s_hi = (int)(((long long)(blockIdx.x + 1) * K) / (int)gridDim.x);
   if (tid == 0) {
     uint32_t tot = 0;
-    for (int s = 0; s < K; ++s) {
+    for (int s = s_lo; s < s_hi; ++s) {
       sf[s] = tot;
       tot += sn[s];
     }
-    sf[K] = tot;
-    if (tot > (uint32_t)kSmallItems) bad_s = 1;  // (the host sized sub_bits for the buffer: a lying header)
+    if (tot > (uint32_t)kSmallItems && !bad_s) bad_s = kSplitRetry;  // more than 1.5 times this CTA's share
   }
   __syncthreads();
   if (bad_s) {
-    if (tid == 0 && status) atomicOr(status, 1u);
+    if (tid == 0 && status) atomicOr(status, bad_s);
     return;
   }
   // ---- this thread's item
   int s = -1;
   uint32_t j = 0;
-  for (int q = 0; q < K; ++q)
+  for (int q = s_lo; q < s_hi; ++q)
     if ((uint32_t)tid >= sf[q] && (uint32_t)tid - sf[q] < sn[q]) {
       s = q;
       j = (uint32_t)tid - sf[q];
@@ -2692,14 +2697,16 @@ size_t decompress_split_work_bytes(uint32_t n_blocks, int K, uint32_t block_size
 // One small buffer (compressed size known to the host): the whole split decode as one CTA.
 // (one SM: 45 us per 100 KiB of raw bytes; the seven launches of the spread form take about 110 us
 // for anything up to a few MiB -- profiles/r2_split_decode.md)
-bool split_small_fits(uint64_t comp_bytes, int K) { return comp_bytes <= (128u << 10) && K < kSmallItems / 2; }
+bool split_small_fits(uint64_t comp_bytes, int K) { return comp_bytes <= (1u << 20) && K < kSmallItems / 2; }
 cudaError_t launch_decompress_split_small(const uint8_t* d_comp, const uint32_t* d_size, uint64_t comp_bytes, int K,
                                           uint8_t* d_raw, uint32_t raw_n, uint32_t* d_status, cudaStream_t st) {
-  // items of 8 * comp_bytes / (kSmallItems - K) bits, rounded up to a multiple of 32, at least 256
-  uint64_t sub = (8u * comp_bytes + (uint64_t)(kSmallItems - K) - 1) / (uint64_t)(kSmallItems - K);
+  const int ctas = K < kSmallMaxCtas ? K : kSmallMaxCtas;
+  // items so that a CTA with 1.5 times its share of the bits still fits: a multiple of 32, at least 384
+  const uint64_t cap = (uint64_t)(kSmallItems - (K + ctas - 1) / ctas);
+  uint64_t sub = (12u * comp_bytes + cap * ctas - 1) / (cap * ctas);
   sub = (sub + 31) & ~(uint64_t)31;
-  if (sub < 256) sub = 256;
-  k_split_small<kSplitBits><<<1, kSmallItems, 0, st>>>(d_comp, d_size, K, d_raw, raw_n, (uint32_t)sub, d_status);
+  if (sub < 384) sub = 384;
+  k_split_small<kSplitBits><<<ctas, kSmallItems, 0, st>>>(d_comp, d_size, K, d_raw, raw_n, (uint32_t)sub, d_status);
   return cudaGetLastError();
 }
 

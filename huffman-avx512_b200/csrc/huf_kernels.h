@@ -44,7 +44,10 @@ cudaError_t launch_decompress_split(const uint8_t* d_comp, const unsigned long l
                                     const uint32_t* d_sizes, uint32_t n_blocks, int K, uint8_t* d_raw, uint64_t raw_n,
                                     uint32_t block_size, uint32_t sub_bits, void* d_work, uint32_t* d_status,
                                     int* launches, cudaStream_t st);
-// The same for ONE buffer of at most 128 KiB compressed, as a single CTA (one launch).
+// The same for ONE buffer of at most 1 MiB compressed as a single launch (up to eight CTAs, whole
+// streams each).  A status of kSplitSmallRetry (bit 1) means that a CTA's streams did not fit its
+// items: nothing usable was written, take launch_decompress_split.
+constexpr uint32_t kSplitSmallRetry = 2u;
 bool split_small_fits(uint64_t comp_bytes, int K);
 cudaError_t launch_decompress_split_small(const uint8_t* d_comp, const uint32_t* d_size, uint64_t comp_bytes, int K,
                                           uint8_t* d_raw, uint32_t raw_n, uint32_t* d_status, cudaStream_t st);

@@ -127,7 +127,7 @@ def test_single_buffer_calls_take_the_split_path(huf, oracle):
         before = huf.launch_count()
         assert huf.decompress(k, comp) == data
         launches = huf.launch_count() - before
-        if len(comp) <= (128 << 10):
+        if len(comp) <= (1 << 20) and n <= (2 << 20):
             assert launches == 1  # the whole split decode as one CTA (k_split_small)
         else:
             assert launches > 1  # plan, scan, passes, item scan, write: not the single launch
@@ -136,7 +136,7 @@ def test_single_buffer_calls_take_the_split_path(huf, oracle):
 @pytest.mark.parametrize("name", ["biased", "english", "seven_bit", "uniform", "two_symbols", "lone_symbol",
                                   "long_codes", "text"])
 def test_small_single_buffers_one_cta_split(huf, oracle, name):
-    """hufb200_decompress of small buffers (k_split_small up to 128 KiB compressed, the spread form above), every K class, ragged sizes."""
+    """hufb200_decompress of small buffers (k_split_small: one launch, up to eight CTAs), every K class, ragged sizes."""
     for k in (1, 3, 4, 8, 16, 32, 48, 64):
         for n in (k * 1024, 100 << 10, 33333 + 1024 * k, (1 << 20) + 17):
             data = _inputs()[name](n)
@@ -191,3 +191,17 @@ def test_split_decode_survives_corrupt_input(huf, oracle):
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     out = codec.decompress(comp, offs, sizes, bs, status=status, split=True)
     assert int(status.item()) == 0 and out[:bs].cpu().numpy().tobytes() == data
+
+
+def test_small_single_buffer_with_unequal_streams_retries(huf, oracle):
+    """Streams of very unequal bit length: the first eighth of the buffer is incompressible, the rest
+    one symbol -- the CTA that gets the first streams has far more than 1.5 times its share of the
+    bits, reports it, and the call falls back to the spread form."""
+    rng = np.random.default_rng(8)
+    n = 1 << 20
+    data = rng.integers(0, 256, n // 8, dtype=np.uint8).tobytes() + b"\x07" * (n - n // 8)
+    for k in (8, 32):
+        comp = oracle.compress(k, data)
+        before = huf.launch_count()
+        assert huf.decompress(k, comp) == data
+        assert huf.launch_count() - before > 1
