@@ -320,6 +320,41 @@ def config1_table(huf, seconds=0.25):
     return out
 
 
+def split_decode_record(huf, raw, dev):
+    """Device-resident decode of inputs with FEW streams (the split decode's ground): the first
+    256 MiB of the bench input as 1 MiB x K = 4 blocks, and its first 64 MiB as ONE buffer of 32
+    streams -- one lane per stream against the split path, CUDA events, output compared."""
+    import torch
+    out = {"unit": "GB/s of raw bytes", "cases": {}}
+    for name, k, bs, n in (("blocks_1MiB_K4_256MiB", 4, 1 << 20, 256 << 20), ("one_buffer_64MiB_K32", 32, 64 << 20, 64 << 20)):
+        n = min(n, raw.numel() // bs * bs)
+        if n == 0:
+            continue
+        codec = huf.BlockCodec(k, bs, device=dev)
+        r = raw[:n]
+        slots, sizes = codec.compress(r)
+        offs = codec.slot_offsets(n)
+        back = torch.empty(n, dtype=torch.uint8, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        work = torch.empty(codec.split_work_bytes(n), dtype=torch.uint8, device=dev)
+        res = {"streams": codec.n_blocks(n) * k}
+        for label, split, reps in (("one_lane_per_stream", False, 1 if n // (codec.n_blocks(n) * k) > (1 << 20) else 3), ("split", True, 5)):
+            codec.decompress(slots, offs, sizes, n, out=back, status=status, split=split, work=work)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                codec.decompress(slots, offs, sizes, n, out=back, status=status, split=split, work=work)
+            b.record()
+            torch.cuda.synchronize()
+            res[label + "_GBps"] = n / (a.elapsed_time(b) / reps * 1e-3) / GB
+            assert torch.equal(back, r) and int(status.item()) == 0, f"{name}/{label}: decode mismatch"
+            back.zero_()
+        out["cases"][name] = res
+        del slots, sizes, back, work
+    return out
+
+
 # ----------------------------------------------------------------------------- parity sample
 
 def parity_sample(args, huf, codec, raw, slots, sizes, status, sh_table):
@@ -701,6 +736,8 @@ def run_ours(args):
         sh_table = shared.pop("_table") if shared else None
         if shared:
             res["shared_table"] = shared
+        if not args.no_shared_leg and world == 1:
+            res["split_decode"] = split_decode_record(huf, raw, dev)
         if not args.no_cpu_baseline and world == 1:
             res["cpu_baseline"] = cpu_reference_run(args, args.cpu_seconds, os.cpu_count() or 1, breadth=True)
             # the checker's other job in this leg: a seeded sample of the blocks the timed steps
