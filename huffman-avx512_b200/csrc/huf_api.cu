@@ -234,6 +234,7 @@ constexpr size_t kContainerHeader = 32;
 // Split decode or one lane per stream?  The split path decodes every bit three times but on as
 // many lanes as the device holds; one lane per stream needs more than about 110 streams per SM (16384 in all) to be faster
 // (measured on the K x block grid, profiles/r2_split_decode.md).  HUFB200_SPLIT=0|1 forces it.
+constexpr size_t kMaxSplitSlice = (size_t)256 << 20;  // split decode: 12 bits per symbol of a stream must stay below 2^32
 bool prefer_split(int k, size_t n_blocks, size_t raw_n) {
   static const int forced = [] {
     const char* e = getenv("HUFB200_SPLIT");
@@ -241,6 +242,7 @@ bool prefer_split(int k, size_t n_blocks, size_t raw_n) {
   }();
   if (raw_n == 0 || n_blocks == 0) return false;
   if (forced >= 0) return forced == 1;
+  if (raw_n / n_blocks / (size_t)k > kMaxSplitSlice) return false;  // (bit positions inside a stream are 32-bit there)
   const size_t streams = n_blocks * (size_t)k;
   return streams <= 16384 && raw_n / streams >= 4096;
 }
@@ -973,6 +975,7 @@ int hufb200_decompress_split_dev(int k, size_t block_size, const uint8_t* d_comp
     return fail(HUFB200_E_INVALID, "n_blocks does not match raw_n / block_size");
   if (n_blocks && (!d_comp || !d_offsets || !d_comp_sizes || !d_raw || !d_work)) return fail(HUFB200_E_INVALID, "null pointer");
   if ((n_blocks * (size_t)k) >> 31) return fail(HUFB200_E_INVALID, "too many streams for the split decode");
+  if (block_size / (size_t)k > kMaxSplitSlice) return fail(HUFB200_E_INVALID, "more than 256 MiB per stream: above the split decode's limit");
   int sms = 0;
   int rc = sm_count(&sms);
   if (rc) return rc;

@@ -1692,7 +1692,7 @@ k_split_plan(const uint8_t* __restrict__ comp, const unsigned long long* __restr
       if (s < K) {
         e_off = end_of(s);
         const uint32_t e_prev = s ? end_of(s - 1) : 0u;
-        good = !(e_off > payload || e_prev > e_off || e_off - e_prev < (uint32_t)kSlop);
+        good = !(e_off > payload || e_prev > e_off || e_off - e_prev < (uint32_t)kSlop || e_off - e_prev >= (1u << 29));
         if (good) {
           bits = 8u * (e_off - e_prev - (uint32_t)kSlop);
           n = (bits + sa.sub_bits - 1) / sa.sub_bits;

@@ -140,6 +140,7 @@ HUFB200_API int hufb200_decompress_blocks_dev(int k, size_t block_size, const ui
  * fall into step after a few codes -- until the starts are consistent (what never falls into step
  * is decoded serially behind the last good item), then written out with one lane per item.
  * d_work: hufb200_decompress_split_work_bytes() bytes, 256-byte aligned, contents irrelevant.
+ * block_size / k <= 256 MiB (bit positions inside a stream are 32-bit here), n_blocks * k < 2^31.
  * hufb200_decompress_prefers_split: the library's own choice between the two (the host-pointer
  * calls apply it themselves). */
 HUFB200_API size_t hufb200_decompress_split_work_bytes(int k, size_t block_size, size_t n_blocks, size_t raw_n);
