@@ -37,6 +37,19 @@ def test_pure_host_functions(huf, oracle):
     assert L.hufb200_table_bytes() == 1024 + 1024 + 256 + 32 + 16  # enc, enc2, sorted_syms, len_count, scalars
 
 
+def test_split_decode_choice_is_host_logic(huf):
+    """hufb200_decompress_prefers_split: few streams in all and long enough slices -> split decode."""
+    L = huf.load()
+    MiB = 1 << 20
+    assert L.hufb200_decompress_prefers_split(32, 1, 64 * MiB) == 1          # one large buffer: 32 streams
+    assert L.hufb200_decompress_prefers_split(4, 1024, 1024 * MiB) == 1      # 1 MiB x 4 blocks: 4096 streams
+    assert L.hufb200_decompress_prefers_split(32, 8192, 1024 * MiB) == 0     # BASELINE config 2: 262144 streams
+    assert L.hufb200_decompress_prefers_split(32, 1, 100 << 10) == 0         # 3200 symbols per stream: too short
+    assert L.hufb200_decompress_prefers_split(1, 1, 1024 * MiB) == 0         # above the split path's per-stream limit
+    assert L.hufb200_decompress_prefers_split(4, 1, 1024 * MiB) == 1
+    assert L.hufb200_decompress_prefers_split(4, 0, 0) == 0
+
+
 def test_bound_covers_worst_case(huf, oracle):
     rng = np.random.default_rng(0)
     for n in (1, 100, 4097):
