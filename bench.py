@@ -231,20 +231,22 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------- config 1
 
-def config1_table(huf, seconds=0.25):
+def config1_table(huf, seconds=0.25, fixture="proba02_100k.bin", label="GenerateProbaData(0.2, 102400), 100 KiB",
+                  large=True):
     """BASELINE config 1, the reference's own benchmark unit (codec/huffman_benchmark.cpp:61-81): ONE
     100 KiB biased buffer (GenerateProbaData(0.2, 102400), tests/golden/proba02_100k.bin) through
     the single-buffer drop-in calls that HuffmanCompressorB200<K>::Compress / Decompress make
     (hufb200_compress / hufb200_decompress, host pointers, copies and synchronisation inside), for
     K in {4,8,16,32,48}: microseconds per call and MiB/s -- beside the reference's scalar / AVX-512
-    paths on the same buffer, one thread, its published method."""
+    paths on the same buffer, one thread, its published method.  With another fixture the same
+    table is the reference's file benchmark (BM_CompressFile / BM_DecompressFile, :218-248)."""
     import numpy as np
     from _cases import golden
     from _libs import Ref, have_ref
-    buf = np.frombuffer(golden("proba02_100k.bin"), dtype=np.uint8)
+    buf = np.frombuffer(golden(fixture), dtype=np.uint8)
     n = buf.size
     L = huf.load()
-    out = {"buffer": "GenerateProbaData(0.2, 102400), 100 KiB", "unit": "MiB/s", "rows": {}}
+    out = {"buffer": label, "unit": "MiB/s", "rows": {}}
     cap = L.hufb200_compress_bound(n, 64) + 64
     comp = np.empty(cap, dtype=np.uint8)
     back = np.empty(n, dtype=np.uint8)
@@ -274,6 +276,26 @@ def config1_table(huf, seconds=0.25):
         out["rows"][f"HuffmanCompressorB200<{k}>"] = res
     # one LARGE buffer through the same two calls (pinned host memory): compress spreads pieces of
     # the K streams over the device; decompress cuts the K streams into items (split decode)
+    if large:
+        _config1_large(huf, L, out, clen, olen)
+    if have_ref():
+        r = Ref()
+        flags = open("/proc/cpuinfo").read()
+        avx = all(f in flags for f in ("avx512f", "avx512bw", "avx512vbmi"))
+        for k in (4, 8, 16, 32, 48):
+            vs = [("HuffmanCompressorMulti", r.SCALAR)]
+            if avx and k % 8 == 0:
+                vs += [("HuffmanCompressorAvxGather", r.GATHER), ("HuffmanCompressorAvxPermute", r.PERMUTE)]
+            for cls, v in vs:
+                c, _ = r.bench(k, v, 0, buf, n, n, 1, 1, seconds)
+                d, _ = r.bench(k, v, 1, buf, n, n, 1, 1, seconds)
+                out["rows"][f"{cls}<{k}>"] = {"compress_MiBps": c / 2 ** 20, "decompress_MiBps": d / 2 ** 20,
+                                              "compress_us_per_call": n / c * 1e6, "decompress_us_per_call": n / d * 1e6,
+                                              "threads": 1}
+    return out
+
+
+def _config1_large(huf, L, out, clen, olen):
     import torch
     from _cases import biased
     nl = 64 << 20
@@ -303,21 +325,6 @@ def config1_table(huf, seconds=0.25):
                                       "note": "both through the host-pointer calls (PCIe inside); decompress = split decode, "
                                               "32 streams cut into items of 4 Kbit, one lane per item"}
     del big, compl, backl
-    if have_ref():
-        r = Ref()
-        flags = open("/proc/cpuinfo").read()
-        avx = all(f in flags for f in ("avx512f", "avx512bw", "avx512vbmi"))
-        for k in (4, 8, 16, 32, 48):
-            vs = [("HuffmanCompressorMulti", r.SCALAR)]
-            if avx and k % 8 == 0:
-                vs += [("HuffmanCompressorAvxGather", r.GATHER), ("HuffmanCompressorAvxPermute", r.PERMUTE)]
-            for cls, v in vs:
-                c, _ = r.bench(k, v, 0, buf, n, n, 1, 1, seconds)
-                d, _ = r.bench(k, v, 1, buf, n, n, 1, 1, seconds)
-                out["rows"][f"{cls}<{k}>"] = {"compress_MiBps": c / 2 ** 20, "decompress_MiBps": d / 2 ** 20,
-                                              "compress_us_per_call": n / c * 1e6, "decompress_us_per_call": n / d * 1e6,
-                                              "threads": 1}
-    return out
 
 
 def split_decode_record(huf, raw, dev):
@@ -745,6 +752,13 @@ def run_ours(args):
             # same for shared-table mode against compress-with-that-table
             res["cpu_baseline"]["parity"] = parity_sample(args, huf, codec, raw, slots, sizes, status, sh_table)
             res["cpu_baseline"]["config1"] = config1_table(huf)
+            try:  # the reference's file benchmark on real text (an extra table: never costs the bench line)
+                res["cpu_baseline"]["config1_file"] = config1_table(
+                    huf, seconds=0.15, fixture="real_text_100k.bin", large=False,
+                    label="real English prose, first 100 KiB (tests/golden/real_text_100k.bin; stands in for enwik8, "
+                          "codec/huffman_benchmark.cpp:218-248)")
+            except Exception as e:  # noqa: BLE001
+                res["cpu_baseline"]["config1_file"] = {"error": repr(e)}
         print(json.dumps(res))
     if world > 1:
         dist.barrier()

@@ -220,6 +220,17 @@ __device__ __forceinline__ uint32_t entry_addr(uint32_t base, uint32_t idx) {
   return a;
 }
 
+template <int M>
+__device__ __forceinline__ uint32_t mad_u32(uint32_t x, uint32_t c) {  // x * M + c, kept a multiply-add (FMA pipe)
+  uint32_t a;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(x), "n"(M), "r"(c));
+  return a;
+}
+__device__ __forceinline__ uint32_t mad_u32_rr(uint32_t x, uint32_t m, uint32_t c) {
+  uint32_t a;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a) : "r"(x), "r"(m), "r"(c));
+  return a;
+}
 // read-only data (the decode table inside the lookup loop): not volatile, no memory clobber, so
 // the compiler may schedule it across the loop's other shared-memory traffic
 __device__ __forceinline__ uint32_t lds_u32_ro(uint32_t addr) {
@@ -1171,6 +1182,15 @@ static_assert(kDecChunk - 1 + 3 * kDecLookups < kDecRow, "a round must not overr
 static_assert(12 * kDecLookups + 31 < 6 * 32, "a round must not consume more than 5 input words");
 constexpr uint32_t kRowWrap = (kDecRow / 4 - 1) * 128;
 constexpr int kDecEmits = (kDecChunk - 1 + 3 * kDecLookups) / kDecChunk;  // most complete chunks a round can leave behind
+// Ring positions inside the lookup loop.  A lane's ring word i sits 128 * i bytes behind its
+// first one (lane-private bank).  The position is kept as a counter in the TOP bits of a register
+// (4 bits for the 16-word input ring, 4 or 5 for the output ring): `+= one` wraps by itself, and
+// the byte offset is one shift that the address add absorbs -- no AND per step.
+constexpr int kInRingBits = 4;
+constexpr uint32_t kInRingBytes = 16 * 32 * 4;  // per warp
+constexpr int kOutRingBits = kDecRow == 64 ? 4 : 5;
+template <int BITS>
+__device__ __forceinline__ uint32_t ring_ofs(uint32_t cnt) { return cnt >> (32 - BITS - 7); }  // 128 * (cnt >> (32 - BITS))
 
 // One thread.  The fixed part of the header is fetched with independent loads up front (a loop
 // that reads a count byte, then decides where the next one is, would chain up to 13 global-memory
@@ -1266,7 +1286,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 // per-CTA scratch behind the tables: the T1 build scratch, later the lane rings and output rows
 __host__ __device__ inline size_t dec_region_bytes(int bpc, int nthreads, int entries) {
   const size_t a = (size_t)bpc * entries;
-  const size_t b = (size_t)(nthreads >> 5) * 16 * 32 * 4 + (((size_t)nthreads * kDecRow + 15) & ~(size_t)15);
+  const size_t b = (size_t)(nthreads >> 5) * kInRingBytes + (((size_t)nthreads * kDecRow + 15) & ~(size_t)15);
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
 
@@ -1461,14 +1481,15 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
       if (active) base += (bi->code_end[l] - bi->code_end[l - 1]) >> (kMaxCodeLen - l);
     }
   }
-  const uint32_t col = smem_u32(region) + (uint32_t)warp * (16 * 32 * 4) + 4u * (uint32_t)lane;  // word i at col + (i & 15) * 128
+  const uint32_t col = smem_u32(region) + (uint32_t)warp * kInRingBytes + 4u * (uint32_t)lane;  // word i at col + (i & 15) * 128
   // output staging ring: word j (4 symbols) of this lane at row + (j & 15) * 128 -- lane-private bank
-  const uint32_t row = smem_u32(region) + (uint32_t)nwarps * (16 * 32 * 4) + (uint32_t)warp * (32 * kDecRow) + 4u * (uint32_t)lane;
+  const uint32_t row = smem_u32(region) + (uint32_t)nwarps * kInRingBytes + (uint32_t)warp * (32 * kDecRow) + 4u * (uint32_t)lane;
   // make the three addresses opaque so that they stay in registers instead of being recomputed
   // from tid / %ctaid inside the lookup loop
   asm volatile("" : "+r"(const_cast<uint32_t&>(t_addr)), "+r"(const_cast<uint32_t&>(col)), "+r"(const_cast<uint32_t&>(row)));
 #pragma unroll
   for (int i = 0; i < kMaxCodeLen - kDecBits; ++i) asm volatile("" : "+r"(tl_addr[i]));
+  const uint32_t one = K >= 1 ? 1u : 0u;  // 1 (K is validated by the entry points), but not a constant the assembler could fold the multiply with
 
   // prime: stage two 32-byte sectors (the whole 16-word ring) and keep the next one in registers.
   // Each top-up takes a full sector, so the kernel does not depend on L1 to serve the other half
@@ -1510,9 +1531,9 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   uint32_t end_acc = end_pos << 6;
   uint32_t full_chunks = end_pos >> 5;                   // chunks that lie entirely inside the slice
   acc |= h0 << 6;
-  uint32_t wofs = (h0 >> 2) * 128;                      // byte offset of the ring word being filled
+  uint32_t wofs = (h0 >> 2) << (32 - kOutRingBits);     // ring word being filled (top-bits counter, see ring_ofs)
+  uint32_t rdo = rd << (32 - kInRingBits);              // next input ring word
   uint32_t chunk = 0;                                   // next 32-byte chunk to write out
-  uint32_t rdo = (rd & 15) * 128;
   // One round = kDecLookups straight-line lookups (no branch per lookup, so consecutive lookups
   // overlap).  CHECKED rounds are the last few of a warp, when some lane may run out of symbols:
   // a lane that has them all sees an all-zero entry, which changes nothing.
@@ -1520,30 +1541,39 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
 #pragma unroll
     for (int it = 0; it < kDecLookups; ++it) {
       const uint32_t win = __funnelshift_l(lo, hi, acc);  // shift amount = acc & 31
-      const uint32_t nxw = lds_u32(col + rdo);  // next ring word, needed only if this lookup crosses a word
+      const uint32_t nxw = lds_u32(col + ring_ofs<kInRingBits>(rdo));  // next ring word, needed only if this lookup crosses a word
       // index = max over the levels, formed on the byte addresses (see build_dtable); signed: a
       // level's base may lie below zero as a shared-window offset
-      int ea = (int)entry_addr(t_addr, win >> (32 - kDecBits));
+      // Level l's entry sits at base_l + 4 * (win >> (32 - l)).  With W = win >> (30 - BITS) the
+      // first three levels are W, 2W and 4W up to the bits below an entry's four bytes (W & 3,
+      // 2 * (W & 1), none): true addresses are multiples of four apart, so those bits never
+      // change which level wins (equal true addresses are the same entry), and the winner is
+      // rounded down to its entry.  One shift (ALU pipe) for three levels instead of one each;
+      // the three multiply-adds run on the FMA pipe.
+      const uint32_t W = win >> (30 - kDecBits);
+      int ea = (int)mad_u32_rr(W, one, t_addr);  // (an add would be fused into the max and put it on the ALU pipe)
+      if constexpr (kDecBits + 1 <= kMaxCodeLen) ea = max(ea, (int)mad_u32<2>(W, tl_addr[0]));
+      if constexpr (kDecBits + 2 <= kMaxCodeLen) ea = max(ea, (int)mad_u32<4>(W, tl_addr[1]));
 #pragma unroll
-      for (int l = kDecBits + 1; l <= kMaxCodeLen; ++l)
+      for (int l = kDecBits + 3; l <= kMaxCodeLen; ++l)
         ea = max(ea, (int)entry_addr(tl_addr[l - kDecBits - 1], win >> (32 - l)));
-      uint32_t e = lds_u32_ro((uint32_t)ea);
+      uint32_t e = lds_u32_ro((uint32_t)ea & ~3u);
       if (decltype(checked)::value && acc >= end_acc) e = 0;
       const uint32_t sh = (acc >> 3) & 0x18u;  // 8 * (position in the ring word being filled)
       const uint32_t old = acc;
       acc += e >> 24;  // bits consumed into bits 0..5, symbol count into bits 6..: the loop-carried chain
       // everything below hangs off that chain
       const uint32_t v = e & 0xffffffu;  // the entry's symbols, unused bytes are zero
-      ob |= v << sh;
+      ob = mad_u32_rr(v, 1u << sh, ob);  // ob | v << sh (the bytes are free) on the FMA pipe
       if ((acc ^ old) & 0x100u) {  // the write position crossed a multiple of 4: one ring word is complete
-        sts_u32(row + wofs, ob);
-        wofs = (wofs + 128) & kRowWrap;
+        sts_u32(row + ring_ofs<kOutRingBits>(wofs), ob);
+        wofs += 1u << (32 - kOutRingBits);
         ob = __funnelshift_l(v, 0, sh);  // the symbols that did not fit: v >> (32 - sh), 0 for sh == 0
       }
       if (acc & 32u) {
         hi = lo;
         lo = nxw;
-        rdo = (rdo + 128) & (15 * 128);
+        rdo += 1u << (32 - kInRingBits);
         acc -= 32;
       }
     }
@@ -1591,7 +1621,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
     const uint32_t rdo0 = rdo;
     if (__all_sync(0xffffffffu, no_stream || acc <= far_acc)) lookups(std::false_type{});
     else lookups(std::true_type{});
-    rd += ((rdo - rdo0) & (15 * 128)) >> 7;  // words consumed by this round (at most 4)
+    rd += (rdo - rdo0) >> (32 - kInRingBits);  // words consumed by this round (at most 4)
     // write out the complete chunks (a round adds at most 3 * kDecLookups bytes)
 #pragma unroll
     for (int t = 0; t < kDecEmits; ++t) {
@@ -1619,7 +1649,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   }
   // tail: the bytes of the last, partial chunk
   if (left) {
-    sts_u32(row + wofs, ob);  // the ring word still being filled
+    sts_u32(row + ring_ofs<kOutRingBits>(wofs), ob);  // the ring word still being filled
     uint32_t p = kDecChunk * chunk;
     if (p < h0) p = h0;
     for (; p < end_pos; ++p) out_al[p] = (uint8_t)lds_u8(row + (((p >> 2) * 128) & kRowWrap) + (p & 3));
@@ -2612,7 +2642,12 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
   // A launch that leaves most of the device empty (a single buffer, a few blocks) gets full-size
   // CTAs: the extra warps have no stream, they only help build the tables and leave.
   if (grid <= 64 && nthreads < kDecMaxThreads) nthreads = kDecMaxThreads;
-  const size_t smem = decompress_smem_bytes_threads(bpc, nthreads, K, block_size);
+  size_t smem = decompress_smem_bytes_threads(bpc, nthreads, K, block_size);
+  static const size_t pad = [] {  // tuning aid: HUFB200_DEC_PAD=bytes of unused shared memory per CTA (lowers residency)
+    const char* e = getenv("HUFB200_DEC_PAD");
+    return e ? (size_t)atoi(e) : (size_t)0;
+  }();
+  smem += pad;
   auto kernel = bits == 9 ? k_decompress_blocks<9> : (bits == 10 ? k_decompress_blocks<10> : k_decompress_blocks<11>);
   {  // opt-in beyond the 48 KiB default: the attribute is per device and per kernel and shared by
      // all host threads, so it is set once per device, to the device's limit -- never per launch
@@ -2627,6 +2662,10 @@ cudaError_t launch_decompress(const uint8_t* d_comp, const unsigned long long* d
       if (e != cudaSuccess) return e;
       e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
       if (e != cudaSuccess) return e;
+      if (const char* c = getenv("HUFB200_DEC_CARVEOUT")) {  // tuning aid: shared-memory carve-out in percent
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+        if (e != cudaSuccess) return e;
+      }
       if (dev < 64) configured[bits - 9].fetch_or(1ull << dev, std::memory_order_release);
     }
   }

@@ -73,6 +73,9 @@ def extra_cases():
     return [
         ("Biased100K", golden("proba02_100k.bin")),
         ("Uniform100K", golden("uniform_100k.bin")),
+        # real English prose, 100 KiB: stand-in for the reference's enwik8 file benchmark
+        # (codec/huffman_benchmark.cpp:218-248); see tests/golden/make_golden.py
+        ("RealText100K", golden("real_text_100k.bin")),
         ("Biased70001", biased(70001, seed=3, p=0.05)),
         ("English50000", english(50000, seed=5)),
         ("OneByte", b"x"),

@@ -30,6 +30,16 @@ def main():
     w("many_random.bin", b"".join(many))
     w("many_random_lens.bin", np.array([len(m) for m in many], dtype="<i4").tobytes())
     w("hist_biased_3125.bin", r.gen_hist_biased(3125))
+    # Real text: the reference's second benchmark table takes the first LEN = 100 KiB of a file
+    # named on the command line (enwik8; codec/huffman_benchmark.cpp:38-58, :218-248, README.md:66-68).
+    # There is no network for enwik8; the stand-in is real English prose this image ships: the
+    # licence texts under /usr/share/common-licenses (verbatim copies are permitted by each of
+    # them), concatenated in name order, first 100 KiB.
+    lic = "/usr/share/common-licenses"
+    names = sorted(n for n in os.listdir(lic) if not os.path.islink(os.path.join(lic, n)))
+    text = b"".join(open(os.path.join(lic, n), "rb").read() for n in names)[: 100 << 10]
+    assert len(text) == 100 << 10
+    w("real_text_100k.bin", text)
 
     from _cases import reference_test_cases, extra_cases, KS  # after the inputs exist
     vectors = {}

@@ -45,16 +45,17 @@ def main():
         gb.append({"name": f"BM_CompressBiasedDeviceBlocks<::hufb200::BlockCodec<{kk}>>", "bytes_per_second": c})
         gb.append({"name": f"BM_DecompressBiasedDeviceBlocks<::hufb200::BlockCodec<{kk}>>", "bytes_per_second": d})
     # BASELINE config 1: the reference's own benchmark unit, one 100 KiB buffer per call
-    c1 = cpu.get("config1", {}).get("rows", {})
-    c1_rows = []
-    for name, r in c1.items():
-        cls = name if name.startswith("HuffmanCompressorB200") else name
-        ns = "::hufb200::" if name.startswith("HuffmanCompressorB200") else "::huffman::"
-        gb.append({"name": f"BM_CompressBiased<{ns}{cls}>", "bytes_per_second": r["compress_MiBps"] * 2 ** 20,
-                   "real_time": r["compress_us_per_call"], "time_unit": "us"})
-        gb.append({"name": f"BM_DecompressBiased<{ns}{cls}>", "bytes_per_second": r["decompress_MiBps"] * 2 ** 20,
-                   "real_time": r["decompress_us_per_call"], "time_unit": "us"})
-        c1_rows.append((name, r))
+    # ... and the same through the reference's file benchmark (BM_CompressFile / BM_DecompressFile,
+    # codec/huffman_benchmark.cpp:218-248) on real text
+    c1_rows, file_rows = [], []
+    for key, bm, dest in (("config1", "Biased", c1_rows), ("config1_file", "File", file_rows)):
+        for name, r in cpu.get(key, {}).get("rows", {}).items():
+            ns = "::hufb200::" if name.startswith("HuffmanCompressorB200") else "::huffman::"
+            gb.append({"name": f"BM_Compress{bm}<{ns}{name}>", "bytes_per_second": r["compress_MiBps"] * 2 ** 20,
+                       "real_time": r["compress_us_per_call"], "time_unit": "us"})
+            gb.append({"name": f"BM_Decompress{bm}<{ns}{name}>", "bytes_per_second": r["decompress_MiBps"] * 2 ** 20,
+                       "real_time": r["decompress_us_per_call"], "time_unit": "us"})
+            dest.append((name, r))
     rows.append(("Huff0", 4, None, None, cpu.get("huff0", "unavailable")))
     if args.json:
         json.dump({"context": {"source": args.bench_json, "metric": bench["metric"]}, "benchmarks": gb},
@@ -64,15 +65,22 @@ def main():
     print("-------|---|---|---|---")
     for m, s, c, d, w in rows:
         print(f"{m} | {s} | {mib(c)} | {mib(d)} | {w}")
-    if c1_rows:
+    for title, table in (
+            ("Config 1: ONE 100 KiB biased buffer per call (codec/huffman_benchmark.cpp:61-81), host pointers, one thread",
+             c1_rows),
+            ("File benchmark: ONE 100 KiB buffer of real English text per call (codec/huffman_benchmark.cpp:218-248; "
+             "tests/golden/real_text_100k.bin stands in for enwik8), host pointers, one thread", file_rows)):
+        if not table:
+            continue
         print()
-        print("Config 1: ONE 100 KiB biased buffer per call (codec/huffman_benchmark.cpp:61-81), host pointers, one thread")
+        print(title)
         print()
-        print("Compressor | Compress | us/call | Decompress | us/call")
-        print("-----------|---|---|---|---")
-        for name, r in c1_rows:
+        print("Compressor | Compress | us/call | Decompress | us/call | compressed bytes")
+        print("-----------|---|---|---|---|---")
+        for name, r in table:
             print(f"{name} | {int(r['compress_MiBps'])} MiB/s | {r['compress_us_per_call']:.1f} | "
-                  f"{int(r['decompress_MiBps'])} MiB/s | {r['decompress_us_per_call']:.1f}")
+                  f"{int(r['decompress_MiBps'])} MiB/s | {r['decompress_us_per_call']:.1f} | "
+                  f"{r.get('compressed_bytes', '')}")
 
 
 if __name__ == "__main__":
