@@ -182,6 +182,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.stop_flag = threading.Event()
+        self.first = threading.Event()  # set once the thread is up and has its first sample
         self.max_mhz = None
         self.ok = False
         try:
@@ -216,7 +217,16 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
+            self.first.set()
             time.sleep(0.01)
+
+    def start_sampling(self):
+        """Starts the thread and returns once it is running: its start-up (thread creation, the first
+        NVML call) must not take the interpreter away from the launch loop inside the timed region --
+        with an empty stream that shows up as an idle GPU in the first step."""
+        self.start()
+        if self.ok:
+            self.first.wait(0.5)
 
     def result(self):
         self.stop_flag.set()
@@ -494,8 +504,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     launches0 = huf.launch_count()
     per_step_events = [[ev(), ev(), ev()] for _ in range(args.steps)]
+    sampler.start_sampling()
     barrier()
-    sampler.start()
     t_start, t_end = ev(), ev()
     t_start.record()
     for s in range(args.steps):
@@ -535,8 +545,8 @@ def run_ours(args):
         s_sampler = ClockSampler(local)
         per = max(1e-3, elapsed_ms / args.steps * 1e-3)
         n_sus = max(args.steps, int(args.sustained_seconds / per) + 1)
+        s_sampler.start_sampling()
         barrier()
-        s_sampler.start()
         s0, s1 = ev(), ev()
         s0.record()
         for _ in range(n_sus):

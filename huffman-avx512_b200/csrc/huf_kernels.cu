@@ -32,6 +32,31 @@ namespace hufb200 {
 // ===========================================================================
 // One `red.shared.add` per byte; the bin address is formed by a byte extract (PRMT) and one
 // shift-add (LEA) on the lane's 32-bit shared-space base.
+// Cache modifiers of the kernels' global accesses.  Every input byte is used once per pass and
+// every output byte is written once, so nothing should take a line of the small L1 that is left
+// next to the shared-memory carve-out (measured: profiles/r2_cache_modifiers.md).
+#ifndef HUF_HIST_LDMOD
+#define HUF_HIST_LDMOD ".L1::no_allocate"
+#endif
+#ifndef HUF_ENC_LDMOD
+#define HUF_ENC_LDMOD ".L1::no_allocate"
+#endif
+#ifndef HUF_COMP_STMOD
+#define HUF_COMP_STMOD ".L1::no_allocate"
+#endif
+__device__ __forceinline__ uint4 ldg16_hist(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global" HUF_HIST_LDMOD ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg16_enc(const void* p) {
+  uint4 v;
+  asm volatile("ld.global" HUF_ENC_LDMOD ".v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_out(uint32_t* p, uint32_t v) {
+  asm volatile("st.global" HUF_COMP_STMOD ".u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void bins_add_word(uint32_t* bins_lane, uint32_t w) {
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(bins_lane);
 #pragma unroll
@@ -78,10 +103,10 @@ __device__ __forceinline__ void bins_accumulate(uint32_t* bins, const uint8_t* p
   uint64_t i = t;
   const uint64_t step = nt;
   if (i + 3 * step < nvec) {  // batches of 4 loads per thread, the next batch in flight while one is counted
-    uint4 a = v[i], b = v[i + step], c = v[i + 2 * step], d = v[i + 3 * step];
+    uint4 a = ldg16_hist(v + i), b = ldg16_hist(v + i + step), c = ldg16_hist(v + i + 2 * step), d = ldg16_hist(v + i + 3 * step);
     i += 4 * step;
     for (; i + 3 * step < nvec; i += 4 * step) {
-      const uint4 a2 = v[i], b2 = v[i + step], c2 = v[i + 2 * step], d2 = v[i + 3 * step];
+      const uint4 a2 = ldg16_hist(v + i), b2 = ldg16_hist(v + i + step), c2 = ldg16_hist(v + i + 2 * step), d2 = ldg16_hist(v + i + 3 * step);
       bins_add_vec(bl, a);
       bins_add_vec(bl, b);
       bins_add_vec(bl, c);
@@ -250,7 +275,7 @@ __device__ __forceinline__ uint4 load16(const uint8_t* sp, uint32_t off, uint32_
                                         const uint8_t* lim) {
   const uint8_t* a = sp + off;
   if (valid >= 16) {
-    if (aligned) return *reinterpret_cast<const uint4*>(a);
+    if (aligned) return ldg16_enc(a);
     const uintptr_t base = (uintptr_t)a & ~(uintptr_t)15;
     if (base + 32 <= (uintptr_t)lim) {
       const uint4 A = *reinterpret_cast<const uint4*>(base);
@@ -666,14 +691,14 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
   for (; rows >= 2; rows -= 2) {
     const uint32_t lo0 = lds_u32(sa), hi0 = lds_u32(sa - 4u);
     const uint32_t lo1 = lds_u32(sa + 128u), hi1 = lds_u32(sa + 124u);
-    *out = __funnelshift_lc(lo0, hi0, sh);
-    *(out - 32) = __funnelshift_lc(lo1, hi1, sh);
+    stg_out(out, __funnelshift_lc(lo0, hi0, sh));
+    stg_out(out - 32, __funnelshift_lc(lo1, hi1, sh));
     out -= 64;
     sa += 256;
   }
   if (rows) {
     const uint32_t lo0 = lds_u32(sa), hi0 = lds_u32(sa - 4u);
-    *out = __funnelshift_lc(lo0, hi0, sh);
+    stg_out(out, __funnelshift_lc(lo0, hi0, sh));
     out -= 32;
     sa += 128;
   }
@@ -682,7 +707,7 @@ __device__ inline void copy_stream_out_warp(uint32_t stage_base, unsigned long l
     const uint32_t m = m0 + lane;
     const uint32_t lo = m < wtot ? lds_u32(sa) : 0u;
     const uint32_t hi = m <= wtot ? lds_u32(sa - 4u) : 0u;
-    if (m <= m_last) *out = __funnelshift_lc(lo, hi, sh);
+    if (m <= m_last) stg_out(out, __funnelshift_lc(lo, hi, sh));
     out -= 32;
     sa += 128;
   }
@@ -1061,7 +1086,7 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
 // Decompress kernel: one lane per stream (DecompressMultiImpl<K, Decoder2x>,
 // codec/huffman.cpp:892-955; ParseCompressedHeader :714-736; Decoder2x :642-704)
 // ===========================================================================
-struct DecBlockInfo {
+struct DecBlockHdr {
   uint32_t ok;
   uint32_t raw_size;
   uint32_t comp_size;
@@ -1071,6 +1096,8 @@ struct DecBlockInfo {
   uint32_t num_syms;
   uint32_t code_end[16];   // left-aligned (12-bit) end of the code range of each length
   uint32_t first_idx[16];  // index into sorted_syms of the first code of each length
+};
+struct DecBlockInfo : DecBlockHdr {
   uint8_t syms[256];       // sorted_syms copied out of the header: the table builder reads shared memory
 };
 
@@ -1095,7 +1122,7 @@ struct DecBlockInfo {
 // L1 (u8 per entry: the first code's own length, 15 = none) is scratch that may be reused
 // afterwards; the first symbol sits in byte 0 of T from the first pass on and never changes.
 template <int BITS, int MAXSYM, bool EXT = false>
-__device__ inline void build_dtable(const DecBlockInfo* bi, const uint8_t* syms, uint32_t* T, uint8_t* L1,
+__device__ inline void build_dtable(const DecBlockHdr* bi, const uint8_t* syms, uint32_t* T, uint8_t* L1,
                                     int tid, int nthreads) {
   constexpr int N = 1 << BITS;
   constexpr int SH = kMaxCodeLen - BITS;
@@ -1196,7 +1223,7 @@ __device__ __forceinline__ uint32_t ring_ofs(uint32_t cnt) { return cnt >> (32 -
 // that reads a count byte, then decides where the next one is, would chain up to 13 global-memory
 // latencies); the symbols are copied by the caller's threads (copy_header_syms) unless copy_syms.
 __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
-                                    DecBlockInfo* bi, bool copy_syms = true) {
+                                    DecBlockHdr* bi, uint8_t* syms_out) {  // syms_out: nullptr = the caller copies them
   bi->ok = 0;
   bi->comp_size = comp_size;
   bi->num_syms = 0;
@@ -1241,25 +1268,39 @@ __device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int 
   bi->payload_off = pos + nsyms + 4u * (uint32_t)(K - 1);
   if (bi->payload_off > comp_size) return;
   bi->num_syms = nsyms;
-  if (copy_syms)
-    for (uint32_t i = 0; i < nsyms; ++i) bi->syms[i] = blk[pos + i];
+  if (syms_out)
+    for (uint32_t i = 0; i < nsyms; ++i) syms_out[i] = blk[pos + i];
   bi->ok = 1;
 }
 // sorted_syms of a parsed header into bi->syms, by `nthreads` threads (bi->num_syms is 0 for a malformed header)
-__device__ __forceinline__ void copy_header_syms(const uint8_t* blk, DecBlockInfo* bi, int tid, int nthreads) {
+__device__ __forceinline__ void copy_header_syms(const uint8_t* blk, const DecBlockHdr* bi, uint8_t* syms, int tid,
+                                                 int nthreads) {
   const uint32_t n = bi->num_syms, off = bi->syms_off;
-  for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)nthreads) bi->syms[i] = blk[off + i];
+  for (uint32_t i = (uint32_t)tid; i < n; i += (uint32_t)nthreads) syms[i] = blk[off + i];
+}
+__device__ inline void parse_header(const uint8_t* blk, uint32_t comp_size, int K, uint32_t expect_raw,
+                                    DecBlockInfo* bi, bool copy_syms = true) {
+  parse_header(blk, comp_size, K, expect_raw, static_cast<DecBlockHdr*>(bi), copy_syms ? bi->syms : nullptr);
+}
+__device__ __forceinline__ void copy_header_syms(const uint8_t* blk, DecBlockInfo* bi, int tid, int nthreads) {
+  copy_header_syms(blk, bi, bi->syms, tid, nthreads);
 }
 
 // 32 bytes per lane in one instruction (256-bit global accesses, sm_100+): a lane's sector or
 // output chunk costs one trip through the load/store pipe instead of two
+#ifndef HUF_DEC_STMOD
+#define HUF_DEC_STMOD ".L1::no_allocate"  // the decoder's 32-byte output stores leave the L1 to its input sectors
+#endif
+#ifndef HUF_DEC_LDMOD
+#define HUF_DEC_LDMOD ""  // tuning aid: cache modifiers of the decoder's sector loads (".L1::no_allocate", ".L2::128B" ...)
+#endif
 struct Sector {
   uint32_t w[8];
 };
 __device__ __forceinline__ Sector ld_sector(uintptr_t addr, uintptr_t lo_lim) {
   Sector s;
   if (addr >= lo_lim) {
-    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global" HUF_DEC_LDMOD ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]), "=r"(s.w[4]), "=r"(s.w[5]), "=r"(s.w[6]),
                    "=r"(s.w[7])
                  : "l"(addr));
@@ -1270,7 +1311,7 @@ __device__ __forceinline__ Sector ld_sector(uintptr_t addr, uintptr_t lo_lim) {
   return s;
 }
 __device__ __forceinline__ void st_chunk32(uint8_t* addr, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+  asm volatile("st.global" HUF_DEC_STMOD ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
@@ -1285,7 +1326,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
 
 // per-CTA scratch behind the tables: the T1 build scratch, later the lane rings and output rows
 __host__ __device__ inline size_t dec_region_bytes(int bpc, int nthreads, int entries) {
-  const size_t a = (size_t)bpc * entries;
+  const size_t a = (size_t)bpc * (entries + 256);  // build scratch: first-code lengths + the header's symbols
   const size_t b = (size_t)(nthreads >> 5) * kInRingBytes + (((size_t)nthreads * kDecRow + 15) & ~(size_t)15);
   return ((a > b ? a : b) + 15) & ~(size_t)15;
 }
@@ -1338,7 +1379,10 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   const int nwarps = nthreads >> 5;
   uint32_t* tables = reinterpret_cast<uint32_t*>(dsm);
   uint8_t* region = dsm + (size_t)bpc * kDecEntries * 4;
-  DecBlockInfo* infos = reinterpret_cast<DecBlockInfo*>(region + dec_region_bytes(bpc, nthreads, kDecEntries));
+  DecBlockHdr* infos = reinterpret_cast<DecBlockHdr*>(region + dec_region_bytes(bpc, nthreads, kDecEntries));
+  // sorted_syms of the CTA's blocks: only the table build reads them, so they sit in its scratch
+  // (behind the bpc first-code-length arrays) and not in the resident part of the CTA's shared memory
+  uint8_t* const hdr_syms = region + (size_t)bpc * kDecEntries;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -1358,12 +1402,12 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   // ---- header parse, one thread per block
   if (tid < bpc) {
     const uint32_t b = b0 + tid;
-    DecBlockInfo* bi = &infos[tid];
+    DecBlockHdr* bi = &infos[tid];
     bi->ok = 0;
     if (b < n_blocks) {
       const uint64_t roff = (uint64_t)b * block_size;
       const uint32_t expect = (uint32_t)((raw_n - roff) < (uint64_t)block_size ? (raw_n - roff) : (uint64_t)block_size);
-      parse_header(comp + offsets[b], comp_sizes[b], K, expect, bi, false);
+      parse_header(comp + offsets[b], comp_sizes[b], K, expect, bi, nullptr);
       if (!bi->ok && status) atomicOr(status, 1u);
     } else {
       bi->num_syms = 0;
@@ -1371,13 +1415,13 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   }
   __syncthreads();
   for (int lb = 0; lb < bpc; ++lb)
-    if (b0 + lb < n_blocks) copy_header_syms(comp + offsets[b0 + lb], &infos[lb], tid, nthreads);
+    if (b0 + lb < n_blocks) copy_header_syms(comp + offsets[b0 + lb], &infos[lb], hdr_syms + 256 * lb, tid, nthreads);
   __syncthreads();
   // ---- decode tables
   for (int lb = 0; lb < bpc; ++lb) {
-    const DecBlockInfo* bi = &infos[lb];
+    const DecBlockHdr* bi = &infos[lb];
     if (b0 + lb < n_blocks && bi->ok && bi->raw_size != 0) {
-      build_dtable<kDecBits, 3, true>(bi, bi->syms, tables + (size_t)lb * kDecEntries,
+      build_dtable<kDecBits, 3, true>(bi, hdr_syms + 256 * lb, tables + (size_t)lb * kDecEntries,
                                 region + (size_t)lb * kDecEntries, tid, nthreads);
     }
   }
@@ -1412,7 +1456,7 @@ k_decompress_blocks(const uint8_t* __restrict__ comp, const unsigned long long* 
   }
   const uint32_t b = b0 + (uint32_t)(kItems ? 0 : lb);
   bool active = (lb < bpc) && (b < n_blocks);
-  const DecBlockInfo* bi = &infos[active ? lb : 0];
+  const DecBlockHdr* bi = &infos[active ? lb : 0];
   active = active && bi->ok && bi->raw_size != 0;
 
   uint32_t left = 0;           // symbols still to produce
@@ -2626,7 +2670,7 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
 
 static size_t decompress_smem_bytes_threads(int bpc, int nthreads, int K, uint32_t block_size) {
   const int entries = dec_entries(dec_bits_for(K, block_size));
-  return (size_t)bpc * entries * 4 + dec_region_bytes(bpc, nthreads, entries) + (size_t)bpc * sizeof(DecBlockInfo);
+  return (size_t)bpc * entries * 4 + dec_region_bytes(bpc, nthreads, entries) + (size_t)bpc * sizeof(DecBlockHdr);
 }
 size_t decompress_smem_bytes(int K, int bpc, uint32_t block_size) {
   return decompress_smem_bytes_threads(bpc, ((K * bpc + 31) / 32) * 32, K, block_size);
@@ -2774,7 +2818,7 @@ cudaError_t launch_decompress_split(const uint8_t* d_comp, const unsigned long l
   // the write pass: the decode kernel with one lane per item
   auto kernel = k_decompress_blocks<kSplitBits, true>;
   const int entries = dec_entries(kSplitBits);
-  const size_t smem = (size_t)entries * 4 + dec_region_bytes(1, kSplitThreads, entries) + sizeof(DecBlockInfo);
+  const size_t smem = (size_t)entries * 4 + dec_region_bytes(1, kSplitThreads, entries) + sizeof(DecBlockHdr);
   {
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
