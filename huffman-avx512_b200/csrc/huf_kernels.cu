@@ -745,7 +745,7 @@ __device__ inline void copy_words_out_warp(uint32_t sb, uint32_t nw_data, uint32
     }
     uint32_t hi = __shfl_up_sync(0xffffffffu, lo, 1);
     if (lane == 0) hi = carry;
-    if (i < nw_emit) *(wend - (m_base + i)) = __funnelshift_lc(lo, hi, sh);
+    if (i < nw_emit) stg_out(wend - (m_base + i), __funnelshift_lc(lo, hi, sh));
     carry = __shfl_sync(0xffffffffu, lo, 31);  // only full rows are followed by another row
   }
 }
