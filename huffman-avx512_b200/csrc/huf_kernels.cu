@@ -215,6 +215,29 @@ struct CompSmem {
   unsigned long long placed[kMaxK];  // mbarriers: [s] completes once per staged block, when region_end[s] is known
 };
 
+// Small blocks (k_compress_small_blocks): a batch of kBatch blocks per CTA and iteration.  Same
+// layout and size as CompSmem, except that the table builds' scratch areas alias the bins /
+// staging union (idle while tables are built) and the room of CompSmem::sc holds two more
+// histograms and tables.
+constexpr int kBatch = 4;
+struct CompSmemBatch {
+  union {
+    uint32_t bins[256 * 32];
+    uint32_t stage[kCompWarps][kStageWords];
+    TableScratch sc[kBatch];  // dirty after a build: zeroed again before the union's next use
+  } u;
+  uint32_t hist[kBatch][256];
+  HufTable tab[kBatch];
+  unsigned long long stream_bits[kMaxK];
+  uint32_t region_end[kMaxK];
+  uint32_t bad;
+  uint32_t blk_new, blk_new2;
+  uint32_t ticket;
+  unsigned long long placed[kMaxK];
+};
+static_assert(sizeof(TableScratch) * kBatch <= sizeof(uint32_t) * 256 * 32, "the scratch areas fit the union");
+static_assert(sizeof(CompSmemBatch) <= sizeof(CompSmem), "the batch kernel keeps the residency of the block kernel");
+
 __device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t s) {  // shift >= 32 gives 0
   uint32_t r;
   asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
@@ -822,8 +845,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {  // 
 // the common shapes carries no code for long streams.
 // Returns whether the block went through the staged mode (the caller counts those blocks: the
 // count's parity is the phase the placement barriers are in).
-template <bool kLongSlices>
-__device__ inline bool encode_block_workers(CompSmem& sm, const HufTable& tab, const uint8_t* raw, uint64_t n,
+template <bool kLongSlices, class Smem>
+__device__ inline bool encode_block_workers(Smem& sm, const HufTable& tab, const uint8_t* raw, uint64_t n,
                                             const uint8_t* src, uint32_t bn, uint32_t block_size, int K,
                                             uint8_t* dst, uint32_t* comp_size_out, uint32_t* status,
                                             uint32_t staged_iter) {
@@ -1072,6 +1095,89 @@ k_compress_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_si
     }
   }
   // the last CTA to finish re-arms the counters for the next launch that uses this pair
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) {
+      counters[0] = 0;
+      counters[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// Small blocks (at most 32 KiB): the table build of a block (12-14 us alone, one warp, serial)
+// takes several times longer than the block's histogram and encode (2-5 us on eight warps), so
+// k_compress_blocks -- one builder warp per CTA, hidden behind ONE block's encode -- runs at the
+// builder's pace.  Here a CTA takes kBatch consecutive blocks per iteration: the workers count
+// them one after the other, then kBatch warps build the kBatch tables AT THE SAME TIME (their
+// scratch areas lie in the bins / staging union, which is idle then), then the workers encode
+// the blocks one after the other.  No warp specialisation beyond the ninth warp taking one of the
+// builds; the CTAs that share an SM are in different phases, so the serial builds of one overlap
+// the histograms and encodes of the others.
+__global__ void __launch_bounds__(kCompThreads, kCompCtasPerSm)
+k_compress_small_blocks(const uint8_t* __restrict__ raw, uint64_t n, uint32_t block_size, int K,
+                        uint32_t n_blocks, uint8_t* __restrict__ out, uint64_t slot_stride,
+                        uint32_t* __restrict__ comp_sizes, uint32_t* __restrict__ status, uint32_t counter_slot) {
+  uint32_t* const counters = g_comp_counters[counter_slot];  // [0] next block, [1] CTAs finished
+  extern __shared__ __align__(1024) uint8_t comp_smem[];
+  CompSmemBatch& sm = *reinterpret_cast<CompSmemBatch*>(comp_smem);
+  if (smem_u32(comp_smem) & 1023u) __trap();
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const bool builder = tid >= kWorkThreads;  // the ninth warp: no histogram or encode work
+  auto block_len = [&](uint32_t blk) -> uint32_t {
+    const uint64_t o = (uint64_t)blk * block_size;
+    return (uint32_t)((n - o) < (uint64_t)block_size ? (n - o) : (uint64_t)block_size);
+  };
+  auto zero_union = [&](int bytes) {
+    uint4* z = reinterpret_cast<uint4*>(&sm.u);
+    for (int i = tid; i < bytes / 16; i += kCompThreads) z[i] = make_uint4(0, 0, 0, 0);
+  };
+  zero_union((int)sizeof(sm.u));
+  if (tid < kMaxK) mbar_init(smem_u32(&sm.placed[tid]), 1);
+  uint32_t staged_iter = 0;
+  for (;;) {
+    __syncthreads();  // the previous batch is done with sm.blk_new; the union is all-zero
+    if (tid == 0) sm.blk_new = atomicAdd(&counters[0], (uint32_t)kBatch);
+    __syncthreads();
+    const uint32_t base = sm.blk_new;
+    if (base >= n_blocks) break;
+    const int nb = (int)(n_blocks - base < (uint32_t)kBatch ? n_blocks - base : (uint32_t)kBatch);
+    // ---- histograms, one block after the other (the workers)
+    if (!builder) {
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t blk = base + (uint32_t)j;
+        bins_accumulate(sm.u.bins, raw + (uint64_t)blk * block_size, block_len(blk), tid, kWorkThreads);
+        worker_sync();
+        if (tid < 256) sm.hist[j][tid] = bins_reduce_clear(sm.u.bins, tid);
+        worker_sync();
+      }
+    }
+    __syncthreads();
+    // ---- the tables, all at once: warp 8 builds block 0's, warps 0.. the others'
+    {
+      const int j = builder ? 0 : warp + 1;
+      if (j < nb) build_table_warp<uint32_t, uint32_t>(sm.hist[j], &sm.tab[j], &sm.u.sc[j]);
+    }
+    __syncthreads();
+    zero_union((int)(sizeof(TableScratch) * kBatch + 15) & ~15);
+    __syncthreads();
+    // ---- encode, one block after the other (the workers)
+    if (!builder) {
+      for (int j = 0; j < nb; ++j) {
+        const uint32_t blk = base + (uint32_t)j;
+        if (tid == 0) {
+          sm.bad = 0;
+          sm.ticket = 0;
+        }
+        worker_sync();
+        if (encode_block_workers<false>(sm, sm.tab[j], raw, n, raw + (uint64_t)blk * block_size, block_len(blk), block_size,
+                                        K, out + (uint64_t)blk * slot_stride, comp_sizes + blk, status, staged_iter))
+          ++staged_iter;
+        worker_sync();  // everybody has read sm.bad / sm.region_end of this block
+      }
+    }
+  }
   if (tid == 0) {
     __threadfence();
     if (atomicAdd(&counters[1], 1u) == gridDim.x - 1) {
@@ -2653,10 +2759,26 @@ cudaError_t launch_compress(const uint8_t* d_raw, uint64_t n, uint32_t block_siz
   const bool long_slices = (block_size + (uint32_t)K - 1) / (uint32_t)K > (uint32_t)kStageSlice;
   auto kernel = long_slices ? k_compress_blocks<true> : k_compress_blocks<false>;
   // the attribute is per device and per kernel: remember where it has been set (bit per ordinal)
-  static std::atomic<unsigned long long> configured[2];
+  static std::atomic<unsigned long long> configured[3];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  // small blocks with tables of their own: batches of blocks with their tables built side by side
+  static const uint32_t batch_max = [] {  // tuning aid: HUFB200_COMP_BATCH_MAX=largest block size of the batch kernel (0 = never)
+    const char* v = getenv("HUFB200_COMP_BATCH_MAX");
+    return v ? (uint32_t)atoi(v) : (32u << 10);
+  }();
+  if (!long_slices && d_table == nullptr && block_size <= batch_max && K <= 32) {  // (K = 48: measured 2 % slower)
+    if (dev >= 64 || !((configured[2].load(std::memory_order_acquire) >> dev) & 1ull)) {
+      e = cudaFuncSetAttribute(k_compress_small_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompSmemBatch));
+      if (e != cudaSuccess) return e;
+      if (dev < 64) configured[2].fetch_or(1ull << dev, std::memory_order_release);
+    }
+    k_compress_small_blocks<<<grid, kCompThreads, sizeof(CompSmemBatch), st>>>(
+        d_raw, n, block_size, K, n_blocks, d_out, slot_stride, d_sizes, d_status,
+        g_counter_slot.fetch_add(1, std::memory_order_relaxed) % kCounterSlots);
+    return cudaGetLastError();
+  }
   if (dev >= 64 || !((configured[long_slices].load(std::memory_order_acquire) >> dev) & 1ull)) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompSmem));
     if (e != cudaSuccess) return e;

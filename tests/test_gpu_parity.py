@@ -179,6 +179,25 @@ def test_block_container_roundtrip(huf, oracle):
     assert huf.decompress_blocks(huf.compress_blocks(32, 131072, b"")) == b""
 
 
+def test_small_block_batches_equal_the_reference(huf, oracle):
+    """Blocks of at most 32 KiB go through k_compress_small_blocks (four blocks per CTA and
+    iteration, their tables built side by side): every block, incl. a ragged last one in a
+    batch that is not full, must equal the reference's bytes."""
+    for k, bs, nblk in ((8, 16384, 37), (32, 32768, 22), (16, 4096, 131), (1, 8192, 9)):
+        data = biased(nblk * bs - 777, seed=100 + k) if k != 16 else english(nblk * bs - 5, seed=3)
+        cont = huf.compress_blocks(k, bs, data)
+        assert huf.decompress_blocks(cont) == data
+        nb = (len(data) + bs - 1) // bs
+        assert nb == nblk
+        sizes = np.frombuffer(cont[32: 32 + 4 * nb], dtype="<u4")
+        pos = 32 + 4 * nb
+        for b in range(nb):
+            blk = cont[pos: pos + int(sizes[b])]
+            pos += int(sizes[b])
+            assert blk == oracle.compress(k, data[b * bs: (b + 1) * bs]), (k, bs, b)
+        assert pos == len(cont)
+
+
 def test_staged_encoder_overflow_fallback(huf, oracle):
     """One slice made only of rare symbols (12-bit codes, > 10 bits/symbol) overflows the per-warp
     staging buffer of the staged encoder and must take the ring path; bytes still equal the oracle."""
