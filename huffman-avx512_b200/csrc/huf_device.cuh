@@ -18,6 +18,9 @@ constexpr uint32_t kEnc2Invalid = 1u << 12;    // enc2[] entry of such a symbol:
 
 // Encode-side table.  Lives in shared memory (per-block tables) or in global
 // memory (shared-table mode, built by k_build_table).
+#ifndef HUF_MERGE_SIMPLE
+#define HUF_MERGE_SIMPLE 1
+#endif
 struct HufTable {
   uint32_t enc[256];         // code right-aligned in bits 0..11, length in bits 16..19
   uint32_t enc2[256];        // the same codes for the staged encoder: code << (32 - len) | len (code top-aligned,
@@ -382,6 +385,36 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
         __syncwarp();
       }
       if (lane == 0) sc->par[0][n_nodes - 1] = (uint16_t)(n_nodes - 1);  // the root points at itself
+#if HUF_MERGE_SIMPLE
+    } else if (lane == 0 && n > 1) {
+      // the plain form: queue heads in two registers, reloaded after the pick that used them.  A
+      // third of the instructions of the look-ahead form below at about the same latency per step
+      // (two dependent shared-memory loads instead of a long select chain); what counts once
+      // the build shares its SM's issue slots with thirty-two worker warps.
+      int ls = n - 1, nh = 0;
+      CountT L = (CountT)(sorted[ls] >> 8), N = 0;
+      for (int m = 0; m < n_nodes; ++m) {
+        CountT sum = 0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const bool leaf = (ls >= 0) && (nh == m || L <= N);  // nodes nh..m-1 are waiting; a leaf wins a tie (:375)
+          if (leaf) {
+            sum += L;
+            sc->leaf_parent[ls] = (uint16_t)m;
+            --ls;
+            L = (CountT)(sorted[ls > 0 ? ls : 0] >> 8);
+          } else {
+            sum += N;
+            sc->par[0][nh] = (uint16_t)m;
+            ++nh;
+            N = tree[nh < n_nodes ? nh : n_nodes - 1];  // stale when nh == m: set below
+          }
+        }
+        tree[m] = sum;
+        if (nh == m) N = sum;  // the new node is the only one waiting
+      }
+      sc->par[0][n_nodes - 1] = (uint16_t)(n_nodes - 1);  // the root points at itself
+#else
     } else if (lane == 0 && n > 1) {
       int ls = n - 1, nh = 0;
       CountT L0 = (CountT)(sorted[ls] >> 8);
@@ -410,6 +443,7 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
         N1 = nh + 1 == m ? sum : N1;
       }
       sc->par[0][n_nodes - 1] = (uint16_t)(n_nodes - 1);  // the root points at itself
+#endif
     }
     __syncwarp();
     // 4. node depths by pointer jumping (8 synchronous rounds cover any depth <= 255), then
