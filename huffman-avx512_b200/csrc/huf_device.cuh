@@ -312,10 +312,12 @@ __device__ __noinline__ void build_table_warp(const CountT* hist, HufTable* tab,
     }
     __syncwarp();
     // 3. two-queue Huffman merge with the reference's tie rule (a leaf is preferred, :370-376):
-    //    inherently serial, so the one lane that runs it gets a branch-free body.  Queue heads
-    //    (two leaves, two nodes) live in registers, the values that could be needed after a pick
-    //    are loaded before it is decided, and whether a head exists is decided by the queue
+    //    inherently serial, one lane.  Whether a queue head exists is decided by the queue
     //    indices, never by its value (u32 weights may wrap like the reference's, :365, :414).
+    //    Two forms of the loop (HUF_MERGE_SIMPLE): heads in registers and reloaded after the pick
+    //    that used them (the default: fewest instructions), or heads AND their successors in
+    //    registers with a branch-free body (loads off the dependent chain, three times the
+    //    instructions).
     const int n_nodes = n - 1;
     // Many leaves of similar weight (incompressible input: 256 symbols, all near n/256) make the
     // merge batchable without changing a single decision: while a node t is waiting, every leaf
