@@ -737,7 +737,6 @@ int hufb200_compress_blocks(int k, size_t block_size, const uint8_t* raw, size_t
                             size_t* out_len) {
   if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
   if (block_size == 0 || block_size > kMaxBlock) return fail(HUFB200_E_INVALID, "block_size outside 1..2^30");
-  if (block_size % 16) return fail(HUFB200_E_INVALID, "block_size must be a multiple of 16");
   if (!out_len || (!raw && n) || (!out && cap)) return fail(HUFB200_E_INVALID, "null pointer");
   const size_t nb = hufb200_blocks_count(n, block_size);
   if (nb >> 31) return fail(HUFB200_E_INVALID, "too many blocks");
@@ -929,8 +928,8 @@ int hufb200_compress_blocks_dev(int k, size_t block_size, const uint8_t* d_raw, 
                                 uint32_t* d_status, void* stream) {
   if (!valid_k(k)) return fail(HUFB200_E_INVALID, "k=%d outside 1..%d", k, HUFB200_MAX_K);
   if (block_size == 0 || block_size > kMaxBlock) return fail(HUFB200_E_INVALID, "block_size outside 1..2^30");
-  if (block_size % 16 || ((uintptr_t)d_raw & 15) || ((uintptr_t)d_out & 15) || slot_stride % 16)
-    return fail(HUFB200_E_INVALID, "block_size, slot_stride, d_raw and d_out must be 16-byte aligned");
+  if (((uintptr_t)d_raw & 15) || ((uintptr_t)d_out & 15) || slot_stride % 16)
+    return fail(HUFB200_E_INVALID, "slot_stride, d_raw and d_out must be 16-byte aligned");
   if (slot_stride < hufb200_slot_stride(block_size, k)) return fail(HUFB200_E_INVALID, "slot_stride too small");
   const size_t nb = hufb200_blocks_count(n, block_size);
   if (nb >> 31) return fail(HUFB200_E_INVALID, "too many blocks");

@@ -67,7 +67,7 @@ def test_argument_validation_needs_no_device(huf):
     assert L.hufb200_decompress(4, buf, 4, buf, 64, C.byref(n)) == -4
     assert b"header" in L.hufb200_last_error()
     assert L.hufb200_container_info(buf, 64, None, None, None, None) == -4
-    assert L.hufb200_compress_blocks(32, 1000, buf, 10, buf, 64, C.byref(n)) == -1  # block % 16
+    assert L.hufb200_compress_blocks(32, 0, buf, 10, buf, 64, C.byref(n)) == -1  # block size 0
 
 
 def test_no_cpu_fallback_without_device(huf):

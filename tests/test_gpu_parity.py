@@ -198,6 +198,23 @@ def test_small_block_batches_equal_the_reference(huf, oracle):
         assert pos == len(cont)
 
 
+def test_block_sizes_off_the_16_byte_grid(huf, oracle):
+    """The container takes any block size (the reference's buffers have no alignment either): blocks
+    then start off a 16-byte boundary in the raw input and in the decoder's output."""
+    for k, bs, n in ((32, 1000, 17_003), (8, 4099, 50_000), (48, 70_001, 300_000), (4, 33, 1_000), (16, 131_073, 400_000)):
+        data = biased(n, seed=bs)
+        cont = huf.compress_blocks(k, bs, data)
+        assert huf.decompress_blocks(cont) == data, (k, bs)
+        nb = (len(data) + bs - 1) // bs
+        sizes = np.frombuffer(cont[32: 32 + 4 * nb], dtype="<u4")
+        pos = 32 + 4 * nb
+        for b in range(nb):
+            blk = cont[pos: pos + int(sizes[b])]
+            pos += int(sizes[b])
+            assert blk == oracle.compress(k, data[b * bs: (b + 1) * bs]), (k, bs, b)
+        assert pos == len(cont)
+
+
 def test_staged_encoder_overflow_fallback(huf, oracle):
     """One slice made only of rare symbols (12-bit codes, > 10 bits/symbol) overflows the per-warp
     staging buffer of the staged encoder and must take the ring path; bytes still equal the oracle."""
